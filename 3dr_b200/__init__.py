@@ -1,0 +1,283 @@
+"""3dr_b200 -- B200-native pyramidal Lucas-Kanade path for kvmanohar22/3DR (ctypes binding of include/dr3lk.h).
+
+The product is the CUDA library `3dr_b200/lib/libdr3lk.so` (hand-written sm_100a kernels behind a C ABI, built by
+`3dr_b200/csrc/Makefile` / `__graft_entry__.build()`); this module only loads it and mirrors the reference's two call
+surfaces for this path with numpy arrays in place of cv::Mat / std::vector:
+
+  * `Context.calc_optical_flow_pyr_lk`  <->  cv::calcOpticalFlowPyrLK   (reference src/initialization.cpp:608-613)
+  * `Context.box_pyramid`               <->  utils::create_img_pyramid  (reference src/utils.cpp:421-430)
+
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked), but creating a
+`Context` without a CUDA device raises, and a missing library raises at import of `lib()`.
+
+The package name starts with a digit, so import it with `importlib.import_module("3dr_b200")`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdr3lk.so")
+
+OK, E_ARG, E_SIZE, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4
+TERM_COUNT, TERM_EPS = 1, 2
+USE_INITIAL_FLOW, GET_MIN_EIGENVALS = 4, 8
+BOX_AUTO_X86, BOX_TRUNC, BOX_SSE2 = 0, 1, 2
+MAX_LEVELS = 16
+
+# every symbol include/dr3lk.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
+    "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
+    "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
+    "dr3lk_build_lk_pyramid",
+]
+
+
+class Dr3lkError(RuntimeError):
+    """Raised where the reference path would throw cv::Exception (or on CUDA failures)."""
+
+    def __init__(self, code, msg):
+        super().__init__("dr3lk error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libdr3lk.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_int, c_size_t, c_double, c_void_p = ctypes.c_int, ctypes.c_size_t, ctypes.c_double, ctypes.c_void_p
+    P = ctypes.POINTER
+    L.dr3lk_create.argtypes = [P(c_void_p), c_int]
+    L.dr3lk_destroy.argtypes = [c_void_p]
+    L.dr3lk_destroy.restype = None
+    L.dr3lk_last_error.argtypes = [c_void_p]
+    L.dr3lk_last_error.restype = ctypes.c_char_p
+    L.dr3lk_set_stream.argtypes = [c_void_p, c_void_p]
+    L.dr3lk_synchronize.argtypes = [c_void_p]
+    L.dr3lk_launch_count.argtypes = [c_void_p]
+    L.dr3lk_launch_count.restype = ctypes.c_uint64
+    L.dr3lk_host_alloc.argtypes = [c_size_t]
+    L.dr3lk_host_alloc.restype = c_void_p
+    L.dr3lk_host_free.argtypes = [c_void_p]
+    L.dr3lk_host_free.restype = None
+    L.dr3lk_box_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, P(c_void_p), c_int]
+    L.dr3lk_box_pyramid_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_int, P(c_void_p), c_int]
+    lk_tail = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_double]  # win_w .. min_eig_threshold
+    L.dr3lk_calc_optical_flow_pyr_lk.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p, c_int] + lk_tail
+    L.dr3lk_track_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p] + lk_tail
+    L.dr3lk_track_batch_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
+    L.dr3lk_lk_level_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, P(c_int), P(c_int)]
+    L.dr3lk_build_lk_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, P(c_void_p),
+                                         P(c_void_p), P(c_int)]
+    _lib = L
+    return L
+
+
+def lk_level_sizes(w, h, win=(21, 21), max_level=3):
+    """[(w_l, h_l)] for l = 0..effective maxLevel (buildOpticalFlowPyramid's early stop)."""
+    n = min(max_level, MAX_LEVELS - 1) + 1
+    ws, hs = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    ml = lib().dr3lk_lk_level_sizes(w, h, win[0], win[1], min(max_level, MAX_LEVELS - 1), ws, hs)
+    return [(ws[l], hs[l]) for l in range(ml + 1)]
+
+
+def _gray(img):
+    img = np.asarray(img)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise Dr3lkError(E_SIZE, "image must be 2-D uint8 (CV_8UC1)")
+    if img.strides[1] != 1 or img.strides[0] < img.shape[1]:
+        img = np.ascontiguousarray(img)
+    return img
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from dr3lk_host_alloc (lets the host-batch path overlap copies)."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = lib().dr3lk_host_alloc(max(nbytes, 1))
+        if not self._ptr:
+            raise Dr3lkError(E_CUDA, "dr3lk_host_alloc(%d) failed" % nbytes)
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().dr3lk_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA device + stream + scratch memory (dr3lk_ctx). Not thread-safe; use one per thread / GPU."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib().dr3lk_create(ctypes.byref(self._h), device)
+        if rc != OK:
+            raise Dr3lkError(rc, lib().dr3lk_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dr3lk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Dr3lkError(rc, lib().dr3lk_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream), or None/0 for the own stream."""
+        self._check(lib().dr3lk_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(lib().dr3lk_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib().dr3lk_launch_count(self._h))
+
+    # ---- utils::create_img_pyramid ------------------------------------------------------------
+    def box_pyramid(self, img, n_levels=3, mode=BOX_AUTO_X86):
+        """Returns [img, level1, ...]; level 0 is the caller's array (shallow, as in the reference)."""
+        img0 = _gray(img)
+        h, w = img0.shape
+        outs, lw, lh = [], w, h
+        for _ in range(1, n_levels):
+            lw, lh = lw // 2, lh // 2
+            outs.append(np.zeros((max(lh, 0), max(lw, 0)), np.uint8))
+        ptrs = (ctypes.c_void_p * max(len(outs), 1))(*[o.ctypes.data for o in outs])
+        self._check(lib().dr3lk_box_pyramid(self._h, img0.ctypes.data, w, h, img0.strides[0], n_levels, ptrs, mode))
+        return [img0] + outs
+
+    def box_pyramid_device(self, img_ptr, w, h, pitch, image_stride, batch, out_ptrs, mode=BOX_AUTO_X86):
+        n_levels = len(out_ptrs) + 1
+        ptrs = (ctypes.c_void_p * max(len(out_ptrs), 1))(*out_ptrs)
+        self._check(lib().dr3lk_box_pyramid_device(self._h, img_ptr, w, h, pitch, image_stride, batch, n_levels, ptrs, mode))
+
+    # ---- the LK pyramids ------------------------------------------------------------------------
+    def build_lk_pyramid(self, img, win=(21, 21), max_level=3, with_derivatives=False):
+        img0 = _gray(img)
+        h, w = img0.shape
+        sizes = lk_level_sizes(w, h, win, max_level)
+        levels = [np.zeros((lh, lw), np.uint8) for (lw, lh) in sizes]
+        derivs = [np.zeros((lh, lw, 2), np.int16) for (lw, lh) in sizes] if with_derivatives else None
+        lp = (ctypes.c_void_p * len(levels))(*[a.ctypes.data for a in levels])
+        dp = (ctypes.c_void_p * len(levels))(*[a.ctypes.data for a in derivs]) if with_derivatives else None
+        ml = ctypes.c_int(-1)
+        self._check(lib().dr3lk_build_lk_pyramid(self._h, img0.ctypes.data, w, h, img0.strides[0], win[0], win[1], max_level,
+                                                 lp, dp, ctypes.byref(ml)))
+        assert ml.value == len(sizes) - 1
+        return (levels, derivs) if with_derivatives else levels
+
+    # ---- cv::calcOpticalFlowPyrLK ---------------------------------------------------------------
+    def calc_optical_flow_pyr_lk(self, prev, nxt, prev_pts, next_pts=None, win=(21, 21), max_level=3,
+                                 criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4, want_err=True):
+        """Same argument meaning as cv2.calcOpticalFlowPyrLK; returns (nextPts (N,2) f32, status (N,) u8, err (N,) f32|None)."""
+        prev, nxt = _gray(prev), _gray(nxt)
+        if prev.shape != nxt.shape:
+            raise Dr3lkError(E_SIZE, "(-215:Assertion failed) prevPyr[level * lvlStep1].size() == nextPyr[level * lvlStep2].size()")
+        h, w = prev.shape
+        pp = np.ascontiguousarray(np.asarray(prev_pts, np.float32).reshape(-1, 2))
+        n = pp.shape[0]
+        if flags & USE_INITIAL_FLOW:
+            if next_pts is None:
+                raise Dr3lkError(E_ARG, "OPTFLOW_USE_INITIAL_FLOW needs nextPts")
+            npts = np.ascontiguousarray(np.asarray(next_pts, np.float32).reshape(-1, 2)).copy()
+            if npts.shape[0] != n:
+                raise Dr3lkError(E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints")
+        else:
+            npts = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32) if want_err else None
+        self._check(lib().dr3lk_calc_optical_flow_pyr_lk(
+            self._h, prev.ctypes.data, prev.strides[0], nxt.ctypes.data, nxt.strides[0], w, h, pp.ctypes.data,
+            npts.ctypes.data, status.ctypes.data, err.ctypes.data if want_err else None, n, win[0], win[1], max_level,
+            criteria[0], criteria[1], float(criteria[2]), flags, float(min_eig_threshold)))
+        return npts, status, err
+
+    def track_batch(self, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,
+                    err_ptr, pts_offset, stats_ptr=None, win=(21, 21), max_level=3,
+                    criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4):
+        """Device-resident batch (integer device pointers, e.g. torch tensor.data_ptr()). Asynchronous."""
+        offs = np.ascontiguousarray(np.asarray(pts_offset, np.int32))
+        assert offs.shape[0] == batch + 1
+        self._check(lib().dr3lk_track_batch(
+            self._h, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,
+            err_ptr or None, offs.ctypes.data, stats_ptr or None, win[0], win[1], max_level, criteria[0], criteria[1],
+            float(criteria[2]), flags, float(min_eig_threshold)))
+
+    def track_batch_host(self, prev, nxt, prev_pts, pts_offset, next_pts=None, win=(21, 21), max_level=3,
+                         criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4, want_err=True,
+                         want_stats=False, chunk_pairs=0, out=None):
+        """Host-buffer batch: prev/nxt (B,H,W) uint8 arrays (any row step), prev_pts (N,2) f32, pts_offset (B+1,) int32.
+        `out` may hold pre-allocated (next_pts, status, err, stats) arrays (e.g. pinned)."""
+        prev, nxt = np.asarray(prev), np.asarray(nxt)
+        assert prev.dtype == np.uint8 and prev.ndim == 3 and prev.shape == nxt.shape and prev.strides == nxt.strides
+        assert prev.strides[2] == 1
+        B, h, w = prev.shape
+        offs = np.ascontiguousarray(np.asarray(pts_offset, np.int32))
+        pp = np.asarray(prev_pts, np.float32).reshape(-1, 2)
+        assert pp.flags.c_contiguous
+        n = pp.shape[0]
+        if out is not None:
+            npts, status, err, stats = out
+        else:
+            npts = np.zeros((n, 2), np.float32)
+            status = np.zeros(n, np.uint8)
+            err = np.zeros(n, np.float32) if want_err else None
+            stats = np.zeros(n, np.uint32) if want_stats else None
+        if flags & USE_INITIAL_FLOW:
+            npts[...] = np.asarray(next_pts, np.float32).reshape(-1, 2)
+        self._check(lib().dr3lk_track_batch_host(
+            self._h, prev.ctypes.data, nxt.ctypes.data, w, h, prev.strides[1], prev.strides[0], B, pp.ctypes.data,
+            npts.ctypes.data, status.ctypes.data, err.ctypes.data if err is not None else None, offs.ctypes.data,
+            stats.ctypes.data if stats is not None else None, chunk_pairs, win[0], win[1], max_level, criteria[0],
+            criteria[1], float(criteria[2]), flags, float(min_eig_threshold)))
+        return npts, status, err, stats
+
+
+def decode_stats(stats):
+    """stats words -> (iterations, template_levels, err_pass) arrays (see dr3lk_track_batch)."""
+    s = np.asarray(stats, np.uint32)
+    return (s & 0xFFFF).astype(np.int64), ((s >> 16) & 0xFF).astype(np.int64), ((s >> 24) & 1).astype(np.int64)
+
+
+def algorithmic_bytes(stats, win):
+    """B_feat = sum_levels(5T + it_l*T) + T*[err pass] + 21, T = (win_w+1)(win_h+1); summed over features."""
+    it, tl, ep = decode_stats(stats)
+    T = (win[0] + 1) * (win[1] + 1)
+    return int((5 * T * tl + T * it + T * ep + 21).sum())

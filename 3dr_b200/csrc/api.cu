@@ -1,0 +1,622 @@
+// C ABI of dr3lk (include/dr3lk.h): context, device scratch management, parameter normalisation and the
+// orchestration of the pyramid + LK kernels.  Host code only; the kernels live in pyramid.cu / lk_*.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dr3lk_internal.cuh"
+
+using namespace dr3lk;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        // grow with slack so that slowly growing workloads do not reallocate every call
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + bytes / 8 + 256);
+        if (e == cudaSuccess) cap = bytes + bytes / 8 + 256;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Sizes / pitches of the Gaussian pyramid calcOpticalFlowPyrLK builds.
+struct PyrLayout {
+    int ml = 0;  // effective maxLevel
+    int w[kMaxLevels], h[kMaxLevels];
+    int pitch[kMaxLevels];   // bytes, 16-B aligned (scratch levels)
+    int dpitch[kMaxLevels];  // ints, 16-B aligned
+    size_t img_bytes[kMaxLevels];   // per image
+    size_t der_ints[kMaxLevels];    // per image
+};
+
+PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
+{
+    PyrLayout P;
+    int ws[kMaxLevels], hs[kMaxLevels];
+    P.ml = dr3lk_lk_level_sizes(w, h, win_w, win_h, std::min(max_level, kMaxLevels - 1), ws, hs);
+    for (int l = 0; l <= P.ml; l++) {
+        P.w[l] = ws[l]; P.h[l] = hs[l];
+        P.pitch[l] = align_up(ws[l], 16);
+        P.dpitch[l] = align_up(ws[l], 4);
+        P.img_bytes[l] = (size_t)P.pitch[l] * hs[l];
+        P.der_ints[l] = (size_t)P.dpitch[l] * hs[l];
+    }
+    return P;
+}
+
+// Device scratch for one batch of frame pairs: Gaussian levels >= 1 of both frames, derivatives of the previous
+// frame at every level, optionally level-0 copies (host-buffer entry points), and the point arrays.
+struct Workspace {
+    DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs;
+    void release() { pyr_prev.release(); pyr_next.release(); deriv.release(); lvl0_prev.release(); lvl0_next.release(); pts.release(); offs.release(); }
+};
+
+struct LKArgs {
+    int win_w, win_h, max_level, crit_type, crit_max_count, flags;
+    double crit_eps, min_eig_threshold;
+};
+
+}  // namespace
+
+struct dr3lk_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    Workspace ws;                 // single-call / device-batch scratch
+    HostBuf pinned;               // staging for the single-pair host call
+    static constexpr int kSlots = 3;
+    Workspace slot_ws[kSlots];    // chunk pipeline of dr3lk_track_batch_host
+    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(dr3lk_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int fail_cuda(dr3lk_ctx* ctx, cudaError_t e, const char* what)
+{
+    // clear the sticky-free error state so a later call can succeed
+    cudaGetLastError();
+    return fail(ctx, DR3LK_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU_TRY(ctx, expr)                                           \
+    do {                                                            \
+        cudaError_t e__ = (expr);                                   \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #expr);  \
+    } while (0)
+
+int check_lk_args(dr3lk_ctx* ctx, int w, int h, const LKArgs& a)
+{
+    // CV_Assert( maxLevel >= 0 && winSize.width > 2 && winSize.height > 2 )
+    if (a.max_level < 0 || a.win_w <= 2 || a.win_h <= 2)
+        return fail(ctx, DR3LK_E_ARG, "(-215:Assertion failed) maxLevel >= 0 && winSize.width > 2 && winSize.height > 2");
+    if (w < 1 || h < 1) return fail(ctx, DR3LK_E_SIZE, "empty image");
+    if ((long long)a.win_w * a.win_h > 96 * 96) return fail(ctx, DR3LK_E_SIZE, "window larger than 96x96 is not supported");
+    return DR3LK_OK;
+}
+
+// Builds both Gaussian pyramids and the Scharr derivatives for `batch` pairs.  prev0/next0: device level-0 images.
+// Fills `lk` level descriptors.  Scratch comes from `W`.
+int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, int pitch0,
+                   size_t stride0, int batch, const PyrLayout& P, LKParams& lk)
+{
+    size_t pyr_bytes = 0, der_ints = 0;
+    size_t lvl_off[kMaxLevels] = {0}, der_off[kMaxLevels] = {0};
+    for (int l = 0; l <= P.ml; l++) {
+        if (l >= 1) { lvl_off[l] = pyr_bytes; pyr_bytes += P.img_bytes[l] * batch; }
+        der_off[l] = der_ints; der_ints += P.der_ints[l] * batch;
+    }
+    cudaSetDevice(ctx->device);
+    if (pyr_bytes) {
+        CU_TRY(ctx, W.pyr_prev.reserve(pyr_bytes));
+        CU_TRY(ctx, W.pyr_next.reserve(pyr_bytes));
+    }
+    CU_TRY(ctx, W.deriv.reserve(der_ints * sizeof(int)));
+
+    for (int l = 0; l <= P.ml; l++) {
+        LevelDesc& d = lk.lv[l];
+        d.w = P.w[l]; d.h = P.h[l];
+        if (l == 0) {
+            d.prev = prev0; d.next = next0;
+            d.pitch_p = d.pitch_n = pitch0;
+            d.prev_stride = d.next_stride = (long long)stride0;
+        } else {
+            d.prev = (const uint8_t*)W.pyr_prev.p + lvl_off[l];
+            d.next = (const uint8_t*)W.pyr_next.p + lvl_off[l];
+            d.pitch_p = d.pitch_n = P.pitch[l];
+            d.prev_stride = d.next_stride = (long long)P.img_bytes[l];
+        }
+        d.deriv = (const int*)W.deriv.p + der_off[l];
+        d.dpitch = P.dpitch[l];
+        d.deriv_stride = (long long)P.der_ints[l];
+    }
+    lk.max_level = P.ml;
+
+    Launch L{stream, cudaSuccess, 0};
+    for (int l = 0; l <= P.ml; l++) {
+        const LevelDesc& s = lk.lv[l];
+        const bool down = l < P.ml;
+        uint8_t* dp = down ? const_cast<uint8_t*>(lk.lv[l + 1].prev) : nullptr;
+        uint8_t* dn = down ? const_cast<uint8_t*>(lk.lv[l + 1].next) : nullptr;
+        launch_pyr_level(L, s.prev, s.w, s.h, s.pitch_p, s.prev_stride, dp, down ? lk.lv[l + 1].pitch_p : 0,
+                         down ? lk.lv[l + 1].prev_stride : 0, const_cast<int*>(s.deriv), s.dpitch, s.deriv_stride, batch);
+        if (down)
+            launch_pyr_level(L, s.next, s.w, s.h, s.pitch_n, s.next_stride, dn, lk.lv[l + 1].pitch_n, lk.lv[l + 1].next_stride,
+                             nullptr, 0, 0, batch);
+    }
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pyramid kernel launch");
+    return DR3LK_OK;
+}
+
+void fill_lk_scalars(LKParams& lk, const LKArgs& a)
+{
+    // parameter normalisation of calcOpticalFlowPyrLK
+    lk.max_count = (a.crit_type & DR3LK_TERM_COUNT) ? std::min(std::max(a.crit_max_count, 0), 100) : 30;
+    double eps = (a.crit_type & DR3LK_TERM_EPS) ? std::min(std::max(a.crit_eps, 0.), 10.) : 0.01;
+    lk.eps2 = eps * eps;
+    lk.min_eig_thr = a.min_eig_threshold;
+    lk.win_w = a.win_w; lk.win_h = a.win_h;
+    lk.flags = a.flags;
+}
+
+int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk)
+{
+    Launch L{stream, cudaSuccess, 0};
+    if (!launch_lk_fast(L, lk)) launch_lk_generic(L, lk);
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "LK kernel launch");
+    return DR3LK_OK;
+}
+
+// Device-resident batch on (W, stream).  pts_offset_dev: device copy of the offsets.
+int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev_dev, const uint8_t* next_dev, int w,
+                       int h, size_t pitch, size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev,
+                       uint8_t* status_dev, float* err_dev, const int* pts_offset_dev, int n_total, uint32_t* stats_dev,
+                       const LKArgs& a)
+{
+    LKParams lk;
+    memset(&lk, 0, sizeof(lk));
+    PyrLayout P = make_layout(w, h, a.win_w, a.win_h, a.max_level);
+    int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, (int)pitch, image_stride, batch, P, lk);
+    if (rc != DR3LK_OK) return rc;
+    fill_lk_scalars(lk, a);
+    lk.prev_pts = (const float2*)prev_pts_dev;
+    lk.next_pts = (float2*)next_pts_dev;
+    lk.status = status_dev;
+    lk.err = err_dev;
+    lk.stats = stats_dev;
+    lk.pts_offset = pts_offset_dev;
+    lk.batch = batch;
+    lk.n_total = n_total;
+    return run_lk(ctx, stream, lk);
+}
+
+int check_offsets(dr3lk_ctx* ctx, const int* pts_offset, int batch)
+{
+    if (!pts_offset || pts_offset[0] != 0) return fail(ctx, DR3LK_E_ARG, "pts_offset[0] must be 0");
+    for (int b = 0; b < batch; b++)
+        if (pts_offset[b + 1] < pts_offset[b]) return fail(ctx, DR3LK_E_ARG, "pts_offset must be non-decreasing");
+    return DR3LK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dr3lk_create(dr3lk_ctx** out, int device)
+{
+    if (!out) return DR3LK_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return DR3LK_E_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return DR3LK_E_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return DR3LK_E_CUDA; }
+    dr3lk_ctx* c = new (std::nothrow) dr3lk_ctx();
+    if (!c) return DR3LK_E_CUDA;
+    c->device = device;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return DR3LK_E_CUDA; }
+    c->stream = c->own_stream;
+    *out = c;
+    return DR3LK_OK;
+}
+
+void dr3lk_destroy(dr3lk_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->ws.release();
+    ctx->pinned.release();
+    for (int i = 0; i < dr3lk_ctx::kSlots; i++) {
+        ctx->slot_ws[i].release();
+        if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* dr3lk_last_error(const dr3lk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return DR3LK_OK;
+}
+
+int dr3lk_synchronize(dr3lk_ctx* ctx)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    cudaSetDevice(ctx->device);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DR3LK_OK;
+}
+
+uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* dr3lk_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void dr3lk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int dr3lk_lk_level_sizes(int w, int h, int win_w, int win_h, int max_level, int* ws, int* hs)
+{
+    // buildOpticalFlowPyramid: level l+1 = ((w+1)/2, (h+1)/2); stop when the NEXT level would not exceed the window
+    int level = 0;
+    for (;; level++) {
+        ws[level] = w; hs[level] = h;
+        if (level >= max_level) break;
+        const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= win_w || nh <= win_h) break;
+        w = nw; h = nh;
+    }
+    return level;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* box pyramid                                                                                     */
+/* ---------------------------------------------------------------------------------------------- */
+
+static int box_level_mode(dr3lk_ctx* ctx, int w, int h, long long stride, int mode, bool aligned16, int* sse2)
+{
+    if (w < 2 || h < 2 || stride < w) return fail(ctx, DR3LK_E_SIZE, "box pyramid: level smaller than 2x2 or step < width");
+    *sse2 = (mode == DR3LK_BOX_SSE2) || (mode == DR3LK_BOX_AUTO_X86 && (w % 16) == 0 && aligned16);
+    if (*sse2) {
+        if (w % 16) return fail(ctx, DR3LK_E_ARG, "box pyramid: SSE2 rounding needs cols % 16 == 0 (src/utils.cpp:389)");
+        if (stride != w) return fail(ctx, DR3LK_E_UNSUPPORTED, "box pyramid: halfSampleSSE2 assumes a continuous image");
+        return DR3LK_OK;
+    }
+    // Scalar walk of reduce_to_half (src/utils.cpp:401-418): make sure the reference itself stays in bounds.
+    const long long out_w = w / 2, out_h = h / 2, end = stride * (long long)h;
+    long long bottom = stride, rows = 0;
+    while (bottom < end) {
+        if (bottom + 2 * out_w - 1 >= end) return fail(ctx, DR3LK_E_UNSUPPORTED, "box pyramid: the reference reads past its input for this shape");
+        bottom += 2 * out_w + stride;
+        rows++;
+    }
+    if (rows > out_h) return fail(ctx, DR3LK_E_UNSUPPORTED, "box pyramid: the reference writes past its output for this shape (odd cols with odd rows)");
+    if (rows < out_h) return fail(ctx, DR3LK_E_UNSUPPORTED, "box pyramid: the reference leaves output rows unwritten for this shape");
+    return DR3LK_OK;
+}
+
+int dr3lk_box_pyramid_device(dr3lk_ctx* ctx, const uint8_t* img_dev, int w, int h, size_t pitch, size_t image_stride, int batch,
+                             int n_levels, uint8_t* const* out_levels_dev, int mode)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (!img_dev || n_levels < 1 || batch < 1 || (n_levels > 1 && !out_levels_dev)) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad argument");
+    if (mode < DR3LK_BOX_AUTO_X86 || mode > DR3LK_BOX_SSE2) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad mode");
+    cudaSetDevice(ctx->device);
+    Launch L{ctx->stream, cudaSuccess, 0};
+    const uint8_t* src = img_dev;
+    long long row_stride = (long long)pitch, img_stride = (long long)image_stride;
+    for (int l = 1; l < n_levels; l++) {
+        int sse2 = 0;
+        int rc = box_level_mode(ctx, w, h, row_stride, mode, true, &sse2);
+        if (rc != DR3LK_OK) return rc;
+        const long long dst_stride = (long long)(w / 2) * (h / 2);
+        launch_box_half(L, src, w, h, row_stride, img_stride, out_levels_dev[l - 1], dst_stride, batch, sse2);
+        src = out_levels_dev[l - 1];
+        w /= 2; h /= 2;
+        row_stride = w; img_stride = dst_stride;
+    }
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "box pyramid kernel launch");
+    return DR3LK_OK;
+}
+
+int dr3lk_box_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, uint8_t* const* out_levels,
+                      int mode)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (!img || n_levels < 1 || (n_levels > 1 && !out_levels)) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad argument");
+    if (mode < DR3LK_BOX_AUTO_X86 || mode > DR3LK_BOX_SSE2) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad mode");
+    if (n_levels == 1) return DR3LK_OK;
+    if (n_levels > kMaxLevels) return fail(ctx, DR3LK_E_ARG, "box pyramid: too many levels");
+    cudaSetDevice(ctx->device);
+    // validate every level first (the reference would have crashed / corrupted memory on the rejected shapes)
+    {
+        int lw = w, lh = h;
+        long long st = (long long)step;
+        bool aligned = (reinterpret_cast<uintptr_t>(img) & 0xF) == 0;  // is_aligned16(in.data), src/utils.cpp:387
+        for (int l = 1; l < n_levels; l++) {
+            int sse2;
+            int rc = box_level_mode(ctx, lw, lh, st, mode, aligned, &sse2);
+            if (rc != DR3LK_OK) return rc;
+            lw /= 2; lh /= 2; st = lw; aligned = true;  // fresh cv::Mat levels are 16-B aligned and continuous
+        }
+    }
+    // level 0 is copied verbatim (h*step bytes, the walk addresses the flat buffer); levels >= 1 are packed behind it
+    const size_t l0_bytes = (size_t)step * (h - 1) + w;  // the last row of an ROI may end before `step`
+    size_t total = align_up_sz(l0_bytes, 256);
+    size_t off[kMaxLevels] = {0};
+    {
+        int lw = w, lh = h;
+        for (int l = 1; l < n_levels; l++) {
+            lw /= 2; lh /= 2;
+            off[l] = total;
+            total += align_up_sz((size_t)lw * lh, 256);
+        }
+    }
+    CU_TRY(ctx, ctx->ws.lvl0_prev.reserve(total));
+    uint8_t* base = (uint8_t*)ctx->ws.lvl0_prev.p;
+    CU_TRY(ctx, cudaMemcpyAsync(base, img, l0_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    Launch L{ctx->stream, cudaSuccess, 0};
+    const uint8_t* src = base;
+    long long row_stride = (long long)step;
+    bool aligned = (reinterpret_cast<uintptr_t>(img) & 0xF) == 0;
+    int lw = w, lh = h;
+    for (int l = 1; l < n_levels; l++) {
+        int sse2 = 0;
+        box_level_mode(ctx, lw, lh, row_stride, mode, aligned, &sse2);
+        launch_box_half(L, src, lw, lh, row_stride, 0, base + off[l], 0, 1, sse2);
+        lw /= 2; lh /= 2;
+        src = base + off[l]; row_stride = lw; aligned = true;
+    }
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "box pyramid kernel launch");
+    lw = w; lh = h;
+    for (int l = 1; l < n_levels; l++) {
+        lw /= 2; lh /= 2;
+        CU_TRY(ctx, cudaMemcpyAsync(out_levels[l - 1], base + off[l], (size_t)lw * lh, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DR3LK_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* LK                                                                                              */
+/* ---------------------------------------------------------------------------------------------- */
+
+int dr3lk_track_batch(dr3lk_ctx* ctx, const uint8_t* prev_dev, const uint8_t* next_dev, int w, int h, size_t pitch,
+                      size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev, uint8_t* status_dev,
+                      float* err_dev, const int* pts_offset, uint32_t* stats_dev, int win_w, int win_h, int max_level,
+                      int crit_type, int crit_max_count, double crit_eps, int flags, double min_eig_threshold)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (batch < 1 || !prev_dev || !next_dev || pitch < (size_t)w) return fail(ctx, DR3LK_E_ARG, "track_batch: bad image arguments");
+    rc = check_offsets(ctx, pts_offset, batch);
+    if (rc != DR3LK_OK) return rc;
+    const int n_total = pts_offset[batch];
+    if (n_total == 0) return DR3LK_OK;
+    if (!prev_pts_dev || !next_pts_dev || !status_dev) return fail(ctx, DR3LK_E_ARG, "track_batch: null point / status buffer");
+    cudaSetDevice(ctx->device);
+    CU_TRY(ctx, ctx->ws.offs.reserve(sizeof(int) * (size_t)(batch + 1)));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->ws.offs.p, pts_offset, sizeof(int) * (size_t)(batch + 1), cudaMemcpyHostToDevice, ctx->stream));
+    return track_batch_device(ctx, ctx->ws, ctx->stream, prev_dev, next_dev, w, h, pitch, image_stride, batch, prev_pts_dev,
+                              next_pts_dev, status_dev, err_dev, (const int*)ctx->ws.offs.p, n_total, stats_dev, a);
+}
+
+int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t prev_step, const uint8_t* next, size_t next_step,
+                                   int w, int h, const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n,
+                                   int win_w, int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps,
+                                   int flags, double min_eig_threshold)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (n < 0) return fail(ctx, DR3LK_E_ARG, "negative point count");
+    if (n == 0) return DR3LK_OK;  // OpenCV releases the outputs and returns
+    if (!prev || !next || prev_step < (size_t)w || next_step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "bad image arguments");
+    if (!prev_pts || !next_pts || !status) return fail(ctx, DR3LK_E_ARG, "null point / status buffer");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    const int pitch0 = align_up(w, 16);
+    const size_t img_bytes = (size_t)pitch0 * h;
+    CU_TRY(ctx, W.lvl0_prev.reserve(img_bytes));
+    CU_TRY(ctx, W.lvl0_next.reserve(img_bytes));
+    // device point block: prev(8n) next(8n) err(4n) stats-less status(n) offsets(8)
+    const size_t o_prev = 0, o_next = 8 * (size_t)n, o_err = 16 * (size_t)n, o_status = 20 * (size_t)n;
+    const size_t pts_bytes = 21 * (size_t)n + 16;
+    CU_TRY(ctx, W.pts.reserve(pts_bytes));
+    CU_TRY(ctx, W.offs.reserve(2 * sizeof(int)));
+    uint8_t* dp = (uint8_t*)W.pts.p;
+    CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_prev.p, pitch0, prev, prev_step, w, h, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_next.p, pitch0, next, next_step, w, h, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(dp + o_prev, prev_pts, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (flags & DR3LK_USE_INITIAL_FLOW)
+        CU_TRY(ctx, cudaMemcpyAsync(dp + o_next, next_pts, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    const int offs[2] = {0, n};
+    CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
+    rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, 1,
+                            (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
+                            (const int*)W.offs.p, n, nullptr, a);
+    if (rc != DR3LK_OK) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(next_pts, dp + o_next, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(status, dp + o_status, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (err) CU_TRY(ctx, cudaMemcpyAsync(err, dp + o_err, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return DR3LK_OK;
+}
+
+int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t step,
+                           size_t image_stride, int batch, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                           const int* pts_offset, uint32_t* stats, int chunk_pairs, int win_w, int win_h, int max_level,
+                           int crit_type, int crit_max_count, double crit_eps, int flags, double min_eig_threshold)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (batch < 1 || !prev || !next || step < (size_t)w || image_stride < step * (size_t)h)
+        return fail(ctx, DR3LK_E_ARG, "track_batch_host: bad image arguments");
+    rc = check_offsets(ctx, pts_offset, batch);
+    if (rc != DR3LK_OK) return rc;
+    if (pts_offset[batch] == 0) return DR3LK_OK;
+    if (!prev_pts || !next_pts || !status) return fail(ctx, DR3LK_E_ARG, "track_batch_host: null point / status buffer");
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < dr3lk_ctx::kSlots; i++)
+        if (!ctx->slot_stream[i]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
+    // make the pipeline streams wait for whatever the caller queued on the context stream
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+
+    if (chunk_pairs <= 0) {
+        // aim at ~64 MB of level-0 pixels per chunk, at least 1 pair, at most the batch split in kSlots*2 pieces
+        const size_t per_pair = 2 * (size_t)w * h;
+        chunk_pairs = (int)std::max<size_t>(1, (64u << 20) / per_pair);
+        chunk_pairs = std::min(chunk_pairs, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
+    }
+    chunk_pairs = std::min(chunk_pairs, batch);
+    const int pitch0 = align_up(w, 16);
+    const size_t img_bytes = (size_t)pitch0 * h;
+    const int n_chunks = (batch + chunk_pairs - 1) / chunk_pairs;
+    std::vector<int> offs_host;  // all chunks' rebased offsets; must outlive the async copies
+    offs_host.reserve((size_t)batch + n_chunks);
+    std::vector<size_t> offs_pos(n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+        const int b0 = c * chunk_pairs, b1 = std::min(batch, b0 + chunk_pairs);
+        offs_pos[c] = offs_host.size();
+        for (int b = b0; b <= b1; b++) offs_host.push_back(pts_offset[b] - pts_offset[b0]);
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        const int slot = c % dr3lk_ctx::kSlots;
+        Workspace& W = ctx->slot_ws[slot];
+        cudaStream_t st = ctx->slot_stream[slot];
+        const int b0 = c * chunk_pairs, b1 = std::min(batch, b0 + chunk_pairs), nb = b1 - b0;
+        const int p0 = pts_offset[b0], n = pts_offset[b1] - p0;
+        if (n == 0) continue;
+        CU_TRY(ctx, W.lvl0_prev.reserve(img_bytes * nb));
+        CU_TRY(ctx, W.lvl0_next.reserve(img_bytes * nb));
+        const size_t o_prev = 0, o_next = 8 * (size_t)n, o_err = 16 * (size_t)n, o_stats = 20 * (size_t)n, o_status = 24 * (size_t)n;
+        CU_TRY(ctx, W.pts.reserve(25 * (size_t)n + 16));
+        CU_TRY(ctx, W.offs.reserve(sizeof(int) * (size_t)(nb + 1)));
+        uint8_t* dp = (uint8_t*)W.pts.p;
+        if (step == (size_t)pitch0 && image_stride == img_bytes) {
+            CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_prev.p, prev + (size_t)b0 * image_stride, img_bytes * nb, cudaMemcpyHostToDevice, st));
+            CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_next.p, next + (size_t)b0 * image_stride, img_bytes * nb, cudaMemcpyHostToDevice, st));
+        } else if (image_stride == step * (size_t)h) {
+            // images back to back: one 2-D copy re-pitches all rows of the chunk
+            CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_prev.p, pitch0, prev + (size_t)b0 * image_stride, step, w, (size_t)h * nb, cudaMemcpyHostToDevice, st));
+            CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_next.p, pitch0, next + (size_t)b0 * image_stride, step, w, (size_t)h * nb, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int b = 0; b < nb; b++) {
+                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.lvl0_prev.p + img_bytes * b, pitch0, prev + (size_t)(b0 + b) * image_stride, step, w, h, cudaMemcpyHostToDevice, st));
+                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.lvl0_next.p + img_bytes * b, pitch0, next + (size_t)(b0 + b) * image_stride, step, w, h, cudaMemcpyHostToDevice, st));
+            }
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(dp + o_prev, prev_pts + 2 * (size_t)p0, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (flags & DR3LK_USE_INITIAL_FLOW)
+            CU_TRY(ctx, cudaMemcpyAsync(dp + o_next, next_pts + 2 * (size_t)p0, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs_host.data() + offs_pos[c], sizeof(int) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
+        rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, nb,
+                                (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
+                                (const int*)W.offs.p, n, stats ? (uint32_t*)(dp + o_stats) : nullptr, a);
+        if (rc != DR3LK_OK) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(next_pts + 2 * (size_t)p0, dp + o_next, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(status + p0, dp + o_status, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (err) CU_TRY(ctx, cudaMemcpyAsync(err + p0, dp + o_err, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (stats) CU_TRY(ctx, cudaMemcpyAsync(stats + p0, dp + o_stats, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < dr3lk_ctx::kSlots; i++) CU_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+    return DR3LK_OK;
+}
+
+int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h, int max_level,
+                           uint8_t* const* out_levels, int16_t* const* out_derivs, int* eff_max_level)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    LKArgs a{win_w, win_h, max_level, 0, 0, 0, 0., 0.};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (!img || step < (size_t)w || !out_levels) return fail(ctx, DR3LK_E_ARG, "build_lk_pyramid: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    const int pitch0 = align_up(w, 16);
+    const size_t img_bytes = (size_t)pitch0 * h;
+    CU_TRY(ctx, W.lvl0_prev.reserve(img_bytes));
+    CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_prev.p, pitch0, img, step, w, h, cudaMemcpyHostToDevice, st));
+    LKParams lk;
+    memset(&lk, 0, sizeof(lk));
+    PyrLayout P = make_layout(w, h, win_w, win_h, max_level);
+    // the "next" pyramid of build_pyramids is pointed at the same image; only the prev outputs are read back
+    rc = build_pyramids(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_prev.p, pitch0, img_bytes, 1, P, lk);
+    if (rc != DR3LK_OK) return rc;
+    for (int l = 0; l <= P.ml; l++) {
+        const LevelDesc& d = lk.lv[l];
+        CU_TRY(ctx, cudaMemcpy2DAsync(out_levels[l], d.w, d.prev, d.pitch_p, d.w, d.h, cudaMemcpyDeviceToHost, st));
+        if (out_derivs)
+            CU_TRY(ctx, cudaMemcpy2DAsync(out_derivs[l], (size_t)d.w * 4, d.deriv, (size_t)d.dpitch * 4, (size_t)d.w * 4, d.h,
+                                          cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (eff_max_level) *eff_max_level = P.ml;
+    return DR3LK_OK;
+}
+
+}  // extern "C"

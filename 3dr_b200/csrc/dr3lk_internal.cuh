@@ -1,0 +1,75 @@
+// Internal declarations shared by the dr3lk CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dr3lk.h"
+
+namespace dr3lk {
+
+constexpr int kMaxLevels = DR3LK_MAX_LEVELS;
+constexpr int W_BITS = 14;  // OpenCV lkpyramid.cpp fixed-point weight bits
+
+// One pyramid level of a batch of frame pairs, as the LK kernels see it.
+struct LevelDesc {
+    const uint8_t* prev;   // [batch][h][pitch_p]  level image of the previous frame
+    const uint8_t* next;   // [batch][h][pitch_n]
+    const int* deriv;      // [batch][h][dpitch]   Scharr (Ix, Iy) as packed int16x2, previous frame only
+    long long prev_stride; // bytes between consecutive pairs
+    long long next_stride;
+    long long deriv_stride;  // ints between consecutive pairs
+    int pitch_p, pitch_n;    // bytes
+    int dpitch;              // ints
+    int w, h;
+};
+
+struct LKParams {
+    LevelDesc lv[kMaxLevels];
+    const float2* prev_pts;
+    float2* next_pts;
+    uint8_t* status;
+    float* err;            // may be null
+    uint32_t* stats;       // may be null
+    const int* pts_offset; // device, batch+1 entries
+    double eps2;           // criteria.epsilon^2
+    double min_eig_thr;
+    int batch;
+    int n_total;
+    int max_level;         // effective
+    int win_w, win_h;
+    int max_count;
+    int flags;
+};
+
+// ---- launchers (each returns the number of kernels it launched, or -1 after setting *err) ----
+struct Launch {
+    cudaStream_t stream;
+    cudaError_t err;
+    int launches;
+};
+
+// pyramid.cu
+// One level step for `n_img` images: reads src level, writes (optionally) the 5-tap down-sampled next level and
+// (optionally) the Scharr derivative of the src level.
+void launch_pyr_level(Launch& L, const uint8_t* src, int w, int h, int src_pitch, long long src_stride, uint8_t* dst,
+                      int dst_pitch, long long dst_stride, int* deriv, int dpitch, long long deriv_stride, int n_img);
+void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
+                     uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding);
+
+// lk_generic.cu
+void launch_lk_generic(Launch& L, const LKParams& p);
+// lk_fast.cu -- returns false when the window size has no specialised kernel
+bool launch_lk_fast(Launch& L, const LKParams& p);
+
+// ---- device helpers ----
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        p = p < 0 ? -p : 2 * len - 2 - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+}  // namespace dr3lk

@@ -1,0 +1,120 @@
+/*
+ * dr3lk.h -- C ABI of the B200-native pyramidal Lucas-Kanade path for kvmanohar22/3DR.
+ *
+ * The reference has no FFI layer; its boundary for this path is two C++ call surfaces:
+ *   (1) cv::calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status, err, winSize, maxLevel,
+ *       criteria, flags, minEigThreshold)          -- called at reference src/initialization.cpp:608-613
+ *   (2) utils::create_img_pyramid(img, n_levels, pyr) -- declared include/utils.hpp:67, defined
+ *       src/utils.cpp:421-430, called from src/frame.cpp:18 (Frame constructor).
+ * Every entry point below names the one it replaces.  Plain pointers and sizes only; all functions
+ * return DR3LK_OK (0) or a negative DR3LK_E_* code and leave a message in dr3lk_last_error().
+ * A context is bound to one CUDA device and one stream; calls on one context must not overlap
+ * (use one context per host thread / per GPU).  There is no CPU fallback: without a usable CUDA
+ * device dr3lk_create fails with DR3LK_E_CUDA.
+ */
+#ifndef DR3LK_H_
+#define DR3LK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR3LK_OK 0
+#define DR3LK_E_ARG (-1)         /* cv::Exception -215 (CV_Assert) in the reference path            */
+#define DR3LK_E_SIZE (-2)        /* image sizes / types differ, or a shape the path cannot represent */
+#define DR3LK_E_CUDA (-3)        /* CUDA runtime error, no device, out of memory                     */
+#define DR3LK_E_UNSUPPORTED (-4) /* shapes on which the reference itself overruns its buffers        */
+
+/* cv::TermCriteria::Type */
+#define DR3LK_TERM_COUNT 1
+#define DR3LK_TERM_EPS 2
+/* cv::OPTFLOW_* flags */
+#define DR3LK_USE_INITIAL_FLOW 4
+#define DR3LK_GET_MIN_EIGENVALS 8
+
+/* rounding / walk of utils::reduce_to_half (reference src/utils.cpp:382-419) */
+#define DR3LK_BOX_AUTO_X86 0 /* as the reference behaves on x86: SSE2 path iff cols % 16 == 0 and 16-B aligned data */
+#define DR3LK_BOX_TRUNC 1    /* scalar / NEON arithmetic (a+b+c+d)/4, src/utils.cpp:411 and 353-372                  */
+#define DR3LK_BOX_SSE2 2     /* halfSampleSSE2 double round-up averaging, src/utils.cpp:324-350                      */
+
+#define DR3LK_MAX_LEVELS 16
+
+typedef struct dr3lk_ctx dr3lk_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int dr3lk_create(dr3lk_ctx** out, int device);
+void dr3lk_destroy(dr3lk_ctx* ctx);
+const char* dr3lk_last_error(const dr3lk_ctx* ctx); /* ctx may be NULL: message of the last failed create */
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream);
+int dr3lk_synchronize(dr3lk_ctx* ctx);
+/* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx);
+/* Pinned host memory for callers that want the host-buffer entry points to overlap copies with compute. */
+void* dr3lk_host_alloc(size_t bytes);
+void dr3lk_host_free(void* p);
+
+/* ---- (2) box pyramid: utils::create_img_pyramid, reference src/utils.cpp:421-430 ------------------ */
+/* Host buffers.  img: h rows of `step` bytes, CV_8UC1.  out_levels[l-1] receives level l (l = 1..n_levels-1),
+ * continuous (w>>l) x (h>>l); level 0 stays the caller's image, as in the reference (shallow copy).
+ * mode AUTO_X86 also looks at the 16-byte alignment of img, like reduce_to_half does. */
+int dr3lk_box_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels,
+                      uint8_t* const* out_levels, int mode);
+/* Device buffers, `batch` images `image_stride` bytes apart.  out_levels_dev[l-1] is a device buffer of
+ * batch * (w>>l)*(h>>l) bytes (images back to back, continuous). */
+int dr3lk_box_pyramid_device(dr3lk_ctx* ctx, const uint8_t* img_dev, int w, int h, size_t pitch, size_t image_stride,
+                             int batch, int n_levels, uint8_t* const* out_levels_dev, int mode);
+
+/* ---- (1) cv::calcOpticalFlowPyrLK, reference call site src/initialization.cpp:608-613 ------------- */
+/* One frame pair, host buffers, OpenCV semantics:
+ *   prev/next  CV_8UC1 w x h, row steps in bytes;  prev_pts n x 2 float (x, y);
+ *   next_pts   n x 2 float, output; also input (initial guess) when flags has DR3LK_USE_INITIAL_FLOW;
+ *   status     n bytes, 1 = tracked;  err n floats or NULL (like an unneeded OutputArray);
+ *   win/max_level/criteria/flags/min_eig_threshold as in OpenCV (maxCount clamped to [0,100], eps to [0,10]).
+ * n == 0 returns DR3LK_OK without touching the outputs.  Errors mirror OpenCV's CV_Assert conditions
+ * (max_level < 0, win <= 2 -> DR3LK_E_ARG).  err of a lost point is written as 0 (OpenCV leaves it
+ * uninitialised).  Synchronous: outputs are complete on return. */
+int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t prev_step, const uint8_t* next,
+                                   size_t next_step, int w, int h, const float* prev_pts, float* next_pts,
+                                   uint8_t* status, float* err, int n, int win_w, int win_h, int max_level,
+                                   int crit_type, int crit_max_count, double crit_eps, int flags,
+                                   double min_eig_threshold);
+
+/* Batched form, device buffers: `batch` independent frame pairs of identical size.  Pair b's images are at
+ * prev_dev + b*image_stride / next_dev + b*image_stride (rows `pitch` bytes apart).  Its points are
+ * prev_pts_dev[pts_offset[b] .. pts_offset[b+1]) (pts_offset: HOST array of batch+1 ints, pts_offset[0] == 0).
+ * stats_dev (optional, may be NULL): one uint32 per point -- bits 0..15 LK iterations executed over all levels,
+ * bits 16..23 number of levels whose template window was built, bit 24 set when the final error pass ran
+ * (the inputs of the algorithmic-bytes model).  Asynchronous on the context's stream. */
+int dr3lk_track_batch(dr3lk_ctx* ctx, const uint8_t* prev_dev, const uint8_t* next_dev, int w, int h, size_t pitch,
+                      size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev,
+                      uint8_t* status_dev, float* err_dev, const int* pts_offset, uint32_t* stats_dev, int win_w,
+                      int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
+                      double min_eig_threshold);
+
+/* Batched form, HOST buffers (the end-to-end path): same layout as dr3lk_track_batch but every pointer is host
+ * memory (pinned memory from dr3lk_host_alloc lets copies overlap compute).  The batch is cut into chunks of
+ * `chunk_pairs` pairs (0 = choose) that are pipelined H2D -> pyramids -> LK -> D2H over several streams.
+ * Synchronous: outputs are complete on return. */
+int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t step,
+                           size_t image_stride, int batch, const float* prev_pts, float* next_pts, uint8_t* status,
+                           float* err, const int* pts_offset, uint32_t* stats, int chunk_pairs, int win_w, int win_h,
+                           int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
+                           double min_eig_threshold);
+
+/* ---- the pyramids calcOpticalFlowPyrLK builds internally (buildOpticalFlowPyramid + calcScharrDeriv) ---- */
+/* Level sizes with OpenCV's early stop; ws/hs need max_level+1 entries.  Returns the effective maxLevel. */
+int dr3lk_lk_level_sizes(int w, int h, int win_w, int win_h, int max_level, int* ws, int* hs);
+/* Host in / host out, for parity checks: out_levels[l] (l = 0..eff. maxLevel) continuous w_l x h_l uint8;
+ * out_derivs[l] continuous w_l x h_l x 2 int16 (Ix, Iy interleaved) or out_derivs == NULL.
+ * *eff_max_level receives the effective maxLevel. */
+int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h,
+                           int max_level, uint8_t* const* out_levels, int16_t* const* out_derivs, int* eff_max_level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DR3LK_H_ */

@@ -1,0 +1,77 @@
+"""Shared helpers for the test-suite (test infrastructure)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "data")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+IMAGES = ["kitti0.png", "kitti1.png", "kitti_000000.png", "sample_gray_500x375.png"]
+
+
+def load_gray(name):
+    path = os.path.join(DATA, name)
+    try:
+        import cv2
+        im = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        assert im is not None, path
+        return im
+    except ImportError:
+        from PIL import Image
+        return np.array(Image.open(path).convert("L"))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def golden_case(name):
+    z = np.load(os.path.join(GOLDEN, "lk_%s.npz" % name))
+    d = {k: z[k] for k in z.files}
+    d["prev"], d["next"] = str(d["prev"]), str(d["next"])
+    d["win"] = (int(d["win"][0]), int(d["win"][1]))
+    d["max_level"] = int(d["max_level"])
+    d["flags"] = int(d["flags"])
+    c = d["crit"]
+    d["crit"] = (int(c[0]), int(c[1]), float(c[2]))
+    d["init"] = d["init"] if d["init"].shape[0] else None
+    return d
+
+
+GOLDEN_CASES = ["c1_default_21x21", "c1_reference_30x30_initflow", "c1_31x31_L4", "c1_mineig_21x21", "oddwidth_21x21",
+                "c1_noisy_init_15x9"]
+
+
+def golden_json(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def compare_lk(p_a, s_a, e_a, p_b, s_b, e_b, converged=None):
+    """Parity metrics between two LK results (north_star gates)."""
+    s_a, s_b = np.asarray(s_a), np.asarray(s_b)
+    both = (s_a == 1) & (s_b == 1)
+    if converged is not None:
+        both_c = both & converged
+    else:
+        both_c = both
+    d = np.linalg.norm(np.asarray(p_a, np.float64) - np.asarray(p_b, np.float64), axis=1)
+    out = {
+        "n": int(len(s_a)),
+        "status_agree": float((s_a == s_b).mean()) if len(s_a) else 1.0,
+        "n_both": int(both.sum()),
+        "max_dpos_converged": float(d[both_c].max()) if both_c.any() else 0.0,
+        "max_dpos_tracked": float(d[both].max()) if both.any() else 0.0,
+        "frac_within_0p01": float((d[both] <= 0.01).mean()) if both.any() else 1.0,
+    }
+    if e_a is not None and e_b is not None:
+        de = np.abs(np.asarray(e_a, np.float64) - np.asarray(e_b, np.float64))
+        out["max_derr"] = float(de[both_c].max()) if both_c.any() else 0.0
+    return out
+
+
+def random_points(rng, w, h, n, margin=40):
+    return np.stack([rng.uniform(-margin, w + margin, n), rng.uniform(-margin, h + margin, n)], 1).astype(np.float32)

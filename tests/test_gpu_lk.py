@@ -1,0 +1,176 @@
+"""GPU parity of the LK tracker: bit-exact against the CPU oracle, within the north_star tolerances against the
+golden vectors of the real OpenCV path, plus edge cases and size-independent properties."""
+import numpy as np
+import pytest
+
+import oracle
+from _common import GOLDEN_CASES, compare_lk, golden_case, golden_json, load_gray, random_points
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_bit_exact(got, exp, what):
+    p, s, e = got
+    po, so, eo = exp
+    assert np.array_equal(s, so), (what, "status", int((s != so).sum()))
+    bad = np.where((p.view(np.uint32) != po.view(np.uint32)).any(axis=1))[0]
+    assert bad.size == 0, (what, "positions differ at", bad[:10], p[bad[:5]], po[bad[:5]])
+    if e is not None:
+        bad = np.where(e.view(np.uint32) != eo.view(np.uint32))[0]
+        assert bad.size == 0, (what, "err differs at", bad[:10], e[bad[:5]], eo[bad[:5]])
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_lk_matches_oracle_bit_exact_and_cv2_golden(ctx, case):
+    g = golden_case(case)
+    a, b = load_gray(g["prev"]), load_gray(g["next"])
+    got = ctx.calc_optical_flow_pyr_lk(a, b, g["prev_pts"], g["init"], g["win"], g["max_level"], g["crit"], g["flags"])
+    po, so, eo, tr = oracle.calc_optical_flow_pyr_lk(a, b, g["prev_pts"], g["init"], g["win"], g["max_level"], g["crit"],
+                                                      g["flags"], trace=True)
+    _assert_bit_exact(got, (po, so, eo), case)
+    max_count = min(max(g["crit"][1], 0), 100) if g["crit"][0] & 1 else 30
+    m = compare_lk(got[0], got[1], got[2], g["next_pts"], g["status"], g["err"], tr["iters"][:, 0] < max_count)
+    assert m["status_agree"] >= 0.999 and m["max_dpos_converged"] <= 0.01 and m["frac_within_0p01"] >= 0.99, m
+
+
+@pytest.mark.parametrize("win,ml,crit,flags", [
+    ((21, 21), 3, (3, 30, 0.01), 0), ((3, 3), 5, (3, 10, 0.01), 0), ((5, 7), 2, (1, 4, 0.0), 0), ((21, 21), 0, (3, 30, 0.01), 0),
+    ((31, 31), 4, (2, 0, 0.03), 0), ((30, 30), 4, (3, 1000, 1e-3), 4), ((21, 21), 3, (3, 0, 0.01), 0), ((45, 33), 3, (3, 30, 0.01), 8),
+    ((21, 21), 3, (3, 30, 0.01), 12)])
+def test_lk_parameter_sweep_bit_exact(ctx, win, ml, crit, flags):
+    a, b = load_gray("kitti3.png"), load_gray("kitti4.png")
+    rng = np.random.default_rng(win[0] * 100 + ml)
+    h, w = a.shape
+    pts = random_points(rng, w, h, 1500)
+    pts[::7] = np.round(pts[::7])          # integer coordinates (weights exactly 1, 0, 0, 0)
+    pts[1::11] = np.round(pts[1::11] * 2) / 2  # half-pixel ties for cvRound
+    init = (pts + rng.normal(0, 2.0, pts.shape)).astype(np.float32) if flags & 4 else None
+    got = ctx.calc_optical_flow_pyr_lk(a, b, pts, init, win, ml, crit, flags)
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, init, win, ml, crit, flags)
+    _assert_bit_exact(got, exp, (win, ml, crit, flags))
+
+
+def test_lk_without_err_output(ctx):
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = random_points(np.random.default_rng(2), 1240, 376, 800)
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, b, pts, want_err=False)
+    po, so, _ = oracle.calc_optical_flow_pyr_lk(a, b, pts, want_err=False)
+    assert e is None and np.array_equal(s, so) and np.array_equal(p.view(np.uint32), po.view(np.uint32))
+
+
+def test_lk_small_images_and_borders(ctx):
+    rng = np.random.default_rng(11)
+    for (h, w, win) in [(24, 24, (21, 21)), (40, 30, (9, 9)), (12, 200, (5, 5)), (23, 23, (21, 21)), (16, 16, (21, 21))]:
+        base = rng.integers(0, 256, (h + 8, w + 8)).astype(np.float32)
+        base = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4  # some smoothness
+        a = base[4:4 + h, 4:4 + w].astype(np.uint8)
+        b = base[3:3 + h, 5:5 + w].astype(np.uint8)
+        pts = random_points(rng, w, h, 300, margin=win[0] + 3)
+        got = ctx.calc_optical_flow_pyr_lk(a, b, pts, None, win, 3, (3, 30, 0.01), 0)
+        exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, win, 3, (3, 30, 0.01), 0)
+        _assert_bit_exact(got, exp, (h, w, win))
+
+
+def test_lk_errors_and_empty(ctx, dr3):
+    a = load_gray("kitti0.png")
+    one = np.zeros((1, 2), np.float32)
+    for kw in [dict(win=(2, 2)), dict(max_level=-1), dict(win=(21, 2))]:
+        with pytest.raises(dr3.Dr3lkError) as e:
+            ctx.calc_optical_flow_pyr_lk(a, a, one, **kw)
+        assert e.value.code == dr3.E_ARG and "maxLevel >= 0 && winSize.width > 2" in str(e.value)
+    with pytest.raises(dr3.Dr3lkError):
+        ctx.calc_optical_flow_pyr_lk(a, a[:, :-1], one)
+    with pytest.raises(dr3.Dr3lkError):
+        ctx.calc_optical_flow_pyr_lk(a, a, one, None, flags=dr3.USE_INITIAL_FLOW)
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, a, np.zeros((0, 2), np.float32))
+    assert p.shape == (0, 2) and s.shape == (0,) and e.shape == (0,)
+    # a context stays usable after an error
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, a, np.array([[300.25, 200.5]], np.float32))
+    assert s[0] == 1 and np.allclose(p[0], [300.25, 200.5], atol=1e-3) and e[0] == 0
+
+
+def test_chain_tracking_counts_match_reference_path(ctx):
+    """C2: kitti0..9 frame-to-frame chain and the reference-style anchored warm-start loop."""
+    g = golden_json("chain_counts.json")
+    frames = [load_gray("kitti%d.png" % i) for i in range(10)]
+    pts = golden_case("c1_default_21x21")["prev_pts"][:g["chain_21x21"][0]]
+    cur, surv = pts, [len(pts)]
+    for i in range(9):
+        p, s, _ = ctx.calc_optical_flow_pyr_lk(frames[i], frames[i + 1], cur)
+        cur = p[s == 1]
+        surv.append(len(cur))
+    # survivor counts can differ from cv2 by a borderline point or two per step (fp32 accumulation order in OpenCV)
+    assert all(abs(x - y) <= max(3, 0.002 * y) for x, y in zip(surv, g["chain_21x21"])), (surv, g["chain_21x21"])
+    ref, curp, anch = pts.copy(), pts.copy(), []
+    for i in range(1, 10):
+        p, s, _ = ctx.calc_optical_flow_pyr_lk(frames[0], frames[i], ref, curp, (30, 30), 4, (3, 1000, 1e-3), 4)
+        ref, curp = ref[s == 1], p[s == 1]
+        anch.append(len(ref))
+    assert all(abs(x - y) <= max(3, 0.002 * y) for x, y in zip(anch, g["anchored_30x30"])), (anch, g["anchored_30x30"])
+
+
+def _torch_batch(ctx, dr3, prev, nxt, pts_list, **kw):
+    import torch
+    B, h, w = prev.shape
+    offs = np.zeros(B + 1, np.int32)
+    offs[1:] = np.cumsum([len(p) for p in pts_list])
+    allp = np.concatenate(pts_list).astype(np.float32)
+    dp, dn = torch.from_numpy(prev).cuda(), torch.from_numpy(nxt).cuda()
+    dpts = torch.from_numpy(allp).cuda()
+    dnext = torch.zeros_like(dpts)
+    dst = torch.zeros(len(allp), dtype=torch.uint8, device="cuda")
+    derr = torch.zeros(len(allp), dtype=torch.float32, device="cuda")
+    dstats = torch.zeros(len(allp), dtype=torch.int32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.track_batch(dp.data_ptr(), dn.data_ptr(), w, h, w, h * w, B, dpts.data_ptr(), dnext.data_ptr(), dst.data_ptr(),
+                    derr.data_ptr(), offs, dstats.data_ptr(), **kw)
+    ctx.synchronize()
+    ctx.set_stream(None)
+    return dnext.cpu().numpy(), dst.cpu().numpy(), derr.cpu().numpy(), dstats.cpu().numpy().view(np.uint32), offs
+
+
+def test_batch_device_and_host_paths_match_single_calls(ctx, dr3):
+    frames = np.stack([load_gray("kitti%d.png" % i) for i in range(6)])
+    prev, nxt = np.ascontiguousarray(frames[:5]), np.ascontiguousarray(frames[1:6])
+    rng = np.random.default_rng(4)
+    pts_list = [random_points(rng, 1240, 376, n) for n in (700, 0, 1, 333, 1024)]  # ragged, incl. an empty pair
+    p, s, e, stats, offs = _torch_batch(ctx, dr3, prev, nxt, pts_list)
+    hp, hs, he, hstats = ctx.track_batch_host(prev, nxt, np.concatenate(pts_list), offs, want_stats=True, chunk_pairs=2)
+    assert np.array_equal(hp.view(np.uint32), p.view(np.uint32)) and np.array_equal(hs, s) and np.array_equal(he, e)
+    assert np.array_equal(hstats, stats)
+    tot_it = 0
+    for b in range(5):
+        sl = slice(offs[b], offs[b + 1])
+        po, so, eo, tr = oracle.calc_optical_flow_pyr_lk(prev[b], nxt[b], pts_list[b], trace=True)
+        _assert_bit_exact((p[sl], s[sl], e[sl]), (po, so, eo), ("pair", b))
+        it, tl, ep = dr3.decode_stats(stats[sl])
+        assert np.array_equal(it, tr["iters"].sum(1)) and np.array_equal(tl, (tr["code"] >= 2).sum(1))
+        tot_it += it.sum()
+    assert tot_it > 0 and dr3.algorithmic_bytes(stats, (21, 21)) > 0
+
+
+def test_properties_full_size_synthetic(ctx, dr3):
+    """Size-independent properties on a full-size (1241x376) synthetic pair: identity gives zero flow and zero error;
+    a pure integer translation is recovered for textured points; results do not depend on batch position."""
+    rng = np.random.default_rng(99)
+    h, w = 376, 1241
+    big = rng.normal(0, 1, (h + 64, w + 64)).astype(np.float32)
+    for _ in range(3):
+        big = (big + np.roll(big, 1, 0) + np.roll(big, -1, 0) + np.roll(big, 1, 1) + np.roll(big, -1, 1)) / 5
+    big = np.clip(128 + 48 * big / big.std(), 0, 255).astype(np.uint8)
+    a = big[32:32 + h, 32:32 + w]
+    b = big[32 - 3:32 - 3 + h, 32 + 5:32 + 5 + w]  # content moves by (-5, +3)
+    xs, ys = np.meshgrid(np.arange(40, w - 40, 16, dtype=np.float32), np.arange(40, h - 40, 16, dtype=np.float32))
+    pts = np.stack([xs.ravel(), ys.ravel()], 1)
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, a, pts)
+    assert s.all() and np.abs(p - pts).max() < 1e-3 and np.abs(e).max() == 0
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, b, pts)
+    assert s.mean() > 0.99
+    d = p[s == 1] - pts[s == 1] - np.array([-5, 3], np.float32)
+    assert np.median(np.abs(d)) < 0.02 and np.percentile(np.abs(d), 99) < 0.2
+    prev = np.ascontiguousarray(np.stack([a, a, a]))
+    nxt = np.ascontiguousarray(np.stack([b, a, b]))
+    bp, bs, be, _, offs = _torch_batch(ctx, dr3, prev, nxt, [pts, pts, pts])
+    n = len(pts)
+    assert np.array_equal(bp[:n].view(np.uint32), p.view(np.uint32)) and np.array_equal(bp[2 * n:].view(np.uint32), p.view(np.uint32))
+    assert np.array_equal(bs[:n], s) and np.array_equal(be[2 * n:], e) and np.abs(bp[n:2 * n] - pts).max() < 1e-3
