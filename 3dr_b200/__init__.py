@@ -29,7 +29,7 @@ MAX_LEVELS = 16
 # every symbol include/dr3lk.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
-    "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
+    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid",
 ]
@@ -66,6 +66,8 @@ def lib():
     L.dr3lk_synchronize.argtypes = [c_void_p]
     L.dr3lk_launch_count.argtypes = [c_void_p]
     L.dr3lk_launch_count.restype = ctypes.c_uint64
+    L.dr3lk_set_profiling.argtypes = [c_void_p, c_int]
+    L.dr3lk_profile_read.argtypes = [c_void_p, P(ctypes.c_float), P(c_int), P(ctypes.c_float), P(c_int)]
     L.dr3lk_host_alloc.argtypes = [c_size_t]
     L.dr3lk_host_alloc.restype = c_void_p
     L.dr3lk_host_free.argtypes = [c_void_p]
@@ -165,6 +167,15 @@ class Context:
 
     def synchronize(self):
         self._check(lib().dr3lk_synchronize(self._h))
+
+    def set_profiling(self, on):
+        self._check(lib().dr3lk_set_profiling(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """(lk_ms, lk_launches, pyramid_ms, pyramid_builds) since the last read; waits for the recorded events."""
+        a, b, c, d = ctypes.c_float(), ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
+        self._check(lib().dr3lk_profile_read(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return a.value, b.value, c.value, d.value
 
     @property
     def launch_count(self):

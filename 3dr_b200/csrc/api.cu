@@ -98,6 +98,9 @@ struct dr3lk_ctx {
     uint64_t launches = 0;
     Workspace ws;                 // single-call / device-batch scratch
     HostBuf pinned;               // staging for the single-pair host call
+    bool profiling = false;
+    struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
+    std::vector<Prof> prof;
     static constexpr int kSlots = 3;
     Workspace slot_ws[kSlots];    // chunk pipeline of dr3lk_track_batch_host
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
@@ -217,8 +220,14 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     LKParams lk;
     memset(&lk, 0, sizeof(lk));
     PyrLayout P = make_layout(w, h, a.win_w, a.win_h, a.max_level);
+    dr3lk_ctx::Prof pr;
+    if (ctx->profiling) {
+        for (int i = 0; i < 3; i++) CU_TRY(ctx, cudaEventCreate(&pr.e[i]));
+        CU_TRY(ctx, cudaEventRecord(pr.e[0], stream));
+    }
     int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, (int)pitch, image_stride, batch, P, lk);
     if (rc != DR3LK_OK) return rc;
+    if (ctx->profiling) CU_TRY(ctx, cudaEventRecord(pr.e[1], stream));
     fill_lk_scalars(lk, a);
     lk.prev_pts = (const float2*)prev_pts_dev;
     lk.next_pts = (float2*)next_pts_dev;
@@ -228,7 +237,12 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     lk.pts_offset = pts_offset_dev;
     lk.batch = batch;
     lk.n_total = n_total;
-    return run_lk(ctx, stream, lk);
+    rc = run_lk(ctx, stream, lk);
+    if (ctx->profiling) {
+        CU_TRY(ctx, cudaEventRecord(pr.e[2], stream));
+        ctx->prof.push_back(pr);
+    }
+    return rc;
 }
 
 int check_offsets(dr3lk_ctx* ctx, const int* pts_offset, int batch)
@@ -300,6 +314,35 @@ int dr3lk_synchronize(dr3lk_ctx* ctx)
 }
 
 uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dr3lk_set_profiling(dr3lk_ctx* ctx, int on)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    ctx->profiling = on != 0;
+    return DR3LK_OK;
+}
+
+int dr3lk_profile_read(dr3lk_ctx* ctx, float* lk_ms, int* lk_launches, float* pyramid_ms, int* pyramid_builds)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    cudaSetDevice(ctx->device);
+    float lk = 0.f, py = 0.f;
+    int n = 0;
+    for (auto& pr : ctx->prof) {
+        CU_TRY(ctx, cudaEventSynchronize(pr.e[2]));
+        float a = 0.f, b = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&a, pr.e[0], pr.e[1]));
+        CU_TRY(ctx, cudaEventElapsedTime(&b, pr.e[1], pr.e[2]));
+        py += a; lk += b; n++;
+        for (int i = 0; i < 3; i++) cudaEventDestroy(pr.e[i]);
+    }
+    ctx->prof.clear();
+    if (lk_ms) *lk_ms = lk;
+    if (lk_launches) *lk_launches = n;
+    if (pyramid_ms) *pyramid_ms = py;
+    if (pyramid_builds) *pyramid_builds = n;
+    return DR3LK_OK;
+}
 
 void* dr3lk_host_alloc(size_t bytes)
 {
@@ -522,8 +565,12 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     cudaSetDevice(ctx->device);
     for (int i = 0; i < dr3lk_ctx::kSlots; i++)
         if (!ctx->slot_stream[i]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
-    // make the pipeline streams wait for whatever the caller queued on the context stream
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the pipeline streams start after whatever the caller queued on the context stream ...
+    cudaEvent_t ev_start;
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventRecord(ev_start, ctx->stream));
+    for (int i = 0; i < dr3lk_ctx::kSlots; i++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ev_start, 0));
+    cudaEventDestroy(ev_start);
 
     if (chunk_pairs <= 0) {
         // aim at ~64 MB of level-0 pixels per chunk, at least 1 pair, at most the batch split in kSlots*2 pieces
@@ -582,7 +629,15 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         if (err) CU_TRY(ctx, cudaMemcpyAsync(err + p0, dp + o_err, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (stats) CU_TRY(ctx, cudaMemcpyAsync(stats + p0, dp + o_stats, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < dr3lk_ctx::kSlots; i++) CU_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+    // ... and the context stream continues after them, so events on it bracket the whole call
+    for (int i = 0; i < dr3lk_ctx::kSlots; i++) {
+        cudaEvent_t ev;
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU_TRY(ctx, cudaEventRecord(ev, ctx->slot_stream[i]));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+        cudaEventDestroy(ev);
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return DR3LK_OK;
 }
 

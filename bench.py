@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- tracked features/sec of the pyramidal-LK hot path (BASELINE.json metric) on N B200s of one node.
+
+Workload ("step" = one pass of the hot path over one batch): config C3 of BASELINE.json -- synthetic 1241x376
+frame pairs, 8192 corners per pair, 4-level 21x21 pyramidal LK (30 iterations, eps 0.01), `--pairs` pairs PER GPU
+(default 4096; weak scaling: every rank tracks its own contiguous block of pairs, no collective on the data path).
+The pairs are `--base-pairs` distinct synthetic pairs (tools/synth.py recipe) tiled to `--pairs`
+separate device buffers, so the per-step working set (~19 GB incl. pyramids) is far larger than L2.
+
+  value     device-resident: inputs already in HBM; per step = pyramids of both frames + Scharr + LK + outputs in HBM.
+  e2e       the same work through the host-buffer C-ABI entry point dr3lk_track_batch_host (pinned HOST images and
+            points in, results back in host memory; H2D/D2H inside the timed region).
+  roofline  LK kernel alone: algorithmic bytes (from the kernel's own per-feature iteration counts)
+            / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the reference's CPU path (cv2.calcOpticalFlowPyrLK, all host threads) on a bounded sample.
+
+`--impl reference` times only that CPU path (rank 0) and prints the same JSON shape.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tracked features/sec at 1/2/4/8 B200 (1241x376, 4-level 21x21 pyramidal LK)"
+UNIT = "features/s"
+WIN, MAX_LEVEL, CRIT, FLAGS = (21, 21), 3, (3, 30, 0.01), 0
+W_IMG, H_IMG, CORNERS = 1241, 376, 8192
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
+    ap.add_argument("--base-pairs", type=int, default=32, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=512, help="pairs per reference-arm step; the cpu_baseline leg uses 3x")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # "under load": samples in the upper half of what was seen (the sampler also sees idle gaps)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(prev, nxt, pts, offs, n_pairs, threads=None):
+    """The reference's CPU path on `n_pairs` pairs: cv2.calcOpticalFlowPyrLK per pair (pyramids included, as the
+    reference calls it with level-0 images only), all host threads.  Falls back to the C oracle port (OpenMP)."""
+    from oracle import cv2_ref
+    import oracle
+    cores = os.cpu_count() or 1
+    n_pairs = min(n_pairs, len(offs) - 1)
+    tracked = feats = 0
+    if cv2_ref.HAVE_CV2:
+        cv2_ref.cv2.setNumThreads(threads or cores)
+        kind, used = "reference", cv2_ref.cv2.getNumThreads()
+        t0 = time.perf_counter()
+        for b in range(n_pairs):
+            p = pts[offs[b]:offs[b + 1]]
+            _, st, _ = cv2_ref.calc_optical_flow_pyr_lk(prev[b], nxt[b], p, None, WIN, MAX_LEVEL, CRIT, FLAGS)
+            tracked += int(st.sum()); feats += len(p)
+        dt = time.perf_counter() - t0
+        what = "cv2 %s calcOpticalFlowPyrLK" % cv2_ref.CV2_VERSION
+    else:
+        kind, used = "port", oracle.num_threads()
+        t0 = time.perf_counter()
+        for b in range(n_pairs):
+            p = pts[offs[b]:offs[b + 1]]
+            _, st, _ = oracle.calc_optical_flow_pyr_lk(prev[b], nxt[b], p, None, WIN, MAX_LEVEL, CRIT, FLAGS)
+            tracked += int(st.sum()); feats += len(p)
+        dt = time.perf_counter() - t0
+        what = "oracle/lk_oracle.c (OpenMP)"
+    return {"tracked": tracked, "features": feats, "seconds": dt, "kind": kind, "cores": used, "what": what, "pairs": n_pairs}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = {"workload": "C3: synthetic 1241x376 frame pairs x 8192 corners, 4-level 21x21 LK (30 it, eps 0.01)",
+           "pairs_per_gpu": args.pairs, "corners_per_pair": CORNERS, "distinct_pairs_per_gpu": args.base_pairs,
+           "sharding": "independent frame pairs per GPU, no collective", "win": list(WIN), "max_level": MAX_LEVEL}
+
+    from tools import synth
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nb = max(1, min(args.base_pairs, args.cpu_sample_pairs))
+        prev, nxt, pts, offs = synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=1000)
+        idx = np.arange(args.cpu_sample_pairs) % nb
+        P, N = prev[idx], nxt[idx]
+        lens = np.diff(offs)[idx]
+        o2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        p2 = np.concatenate([pts[offs[i]:offs[i + 1]] for i in idx])
+        for _ in range(args.warmup):
+            cpu_reference(P, N, p2, o2, min(8, args.cpu_sample_pairs))
+        tot_t = tot_tr = tot_f = 0
+        r = None
+        for _ in range(args.steps):
+            r = cpu_reference(P, N, p2, o2, args.cpu_sample_pairs)
+            tot_t += r["seconds"]; tot_tr += r["tracked"]; tot_f += r["features"]
+        val = tot_tr / tot_t
+        sample = "%d pairs x %d corners per step (bounded sample of the %d-pair workload), %s" % (args.cpu_sample_pairs, CORNERS, args.pairs, r["what"])
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int32 fixed-point + fp32 solve", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "submitted_features_per_s": tot_f / tot_t}))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    dr3 = importlib.import_module("3dr_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    nb = max(1, min(args.base_pairs, args.pairs))
+    prev_b, next_b, pts_b, offs_b = synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=1000 + rank * nb)
+    idx = np.arange(args.pairs) % nb
+    lens = np.diff(offs_b)[idx]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    pts = np.concatenate([pts_b[offs_b[i]:offs_b[i + 1]] for i in idx]).astype(np.float32)
+    n_feat = int(offs[-1])
+    t_idx = torch.from_numpy(idx).to(dev)
+    prev_d = torch.from_numpy(prev_b).to(dev)[t_idx].contiguous()   # (pairs, H, W) distinct device buffers
+    next_d = torch.from_numpy(next_b).to(dev)[t_idx].contiguous()
+    pts_d = torch.from_numpy(pts).to(dev)
+    nxt_d = torch.zeros_like(pts_d)
+    st_d = torch.zeros(n_feat, dtype=torch.uint8, device=dev)
+    err_d = torch.zeros(n_feat, dtype=torch.float32, device=dev)
+    stats_d = torch.zeros(n_feat, dtype=torch.int32, device=dev)
+
+    ctx = dr3.Context(local_rank)
+    # a dedicated (non-default) stream shared by torch and the library, so the CUDA events below see the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    def step_device(stats=False):
+        ctx.track_batch(prev_d.data_ptr(), next_d.data_ptr(), W_IMG, H_IMG, W_IMG, W_IMG * H_IMG, args.pairs, pts_d.data_ptr(),
+                        nxt_d.data_ptr(), st_d.data_ptr(), err_d.data_ptr(), offs, stats_d.data_ptr() if stats else None,
+                        WIN, MAX_LEVEL, CRIT, FLAGS)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing (value) + LK-kernel roofline
+    for _ in range(max(args.warmup, 1)):
+        step_device(stats=True)
+    torch.cuda.synchronize()
+    tracked_per_step = int(st_d.sum().item())
+    stats_h = stats_d.cpu().numpy().view(np.uint32)
+    alg_bytes = dr3.algorithmic_bytes(stats_h, WIN)
+    iters_per_feat = float(dr3.decode_stats(stats_h)[0].mean())
+    ctx.profile_read()
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count - launches0
+    lk_ms, lk_n, pyr_ms, _ = ctx.profile_read()
+    ctx.set_profiling(False)
+    tracked_all = sum_over_ranks(tracked_per_step)
+    feats_all = sum_over_ranks(n_feat)
+    value = tracked_all * args.steps / (ms_total * 1e-3)
+    hbm_peak, peak_src = peaks()
+    lk_ms_avg = lk_ms / max(lk_n, 1)
+    achieved = alg_bytes / (lk_ms_avg * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "lk_track (LK kernel alone, all levels in one launch)", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "lk_ms_per_launch": lk_ms_avg, "pyramid_ms_per_step": pyr_ms / max(lk_n, 1),
+            "lk_iterations_per_feature": iters_per_feat,
+            "note": "algorithmic bytes = sum over features of (5T*levels_with_template + T*iterations + T*err_pass + 21), T=(21+1)^2 "
+                    "(SURVEY.md 8d); the kernel's working set is L2-resident so DRAM traffic is far below this"}
+
+    # ---- end to end through the host-buffer C ABI
+    e2e = None
+    if not args.no_e2e:
+        hp = dr3.PinnedArray((args.pairs, H_IMG, W_IMG), np.uint8)
+        hn = dr3.PinnedArray((args.pairs, H_IMG, W_IMG), np.uint8)
+        hpts = dr3.PinnedArray((n_feat, 2), np.float32)
+        o_np, o_st, o_err = dr3.PinnedArray((n_feat, 2), np.float32), dr3.PinnedArray((n_feat,), np.uint8), dr3.PinnedArray((n_feat,), np.float32)
+        for i in range(nb):
+            sel = np.where(idx == i)[0]
+            hp.array[sel] = prev_b[i]; hn.array[sel] = next_b[i]
+        hpts.array[...] = pts
+
+        def step_host():
+            return ctx.track_batch_host(hp.array, hn.array, hpts.array, offs, None, WIN, MAX_LEVEL, CRIT, FLAGS,
+                                        out=(o_np.array, o_st.array, o_err.array, None))
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_host()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+        wall = max_over_ranks(wall)
+        tracked_host = sum_over_ranks(int(o_st.array.sum()))
+        # parity of the two entry points on the same inputs
+        same = bool(np.array_equal(o_st.array, st_d.cpu().numpy()) and np.array_equal(o_np.array.view(np.uint32), nxt_d.cpu().numpy().view(np.uint32)))
+        e2e = {"value": tracked_host * args.steps / wall, "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * args.pairs * H_IMG * W_IMG + 8 * n_feat + 4 * (args.pairs + 1)),
+               "d2h_bytes_per_step": int(13 * n_feat), "ms_per_step": 1e3 * wall / args.steps, "timer": "host wall clock around the synchronous call, max over ranks",
+               "cuda_event_ms_per_step": ms_e2e / args.steps, "api": "dr3lk_track_batch_host (pinned host buffers)",
+               "matches_device_path": same}
+        for a in (hp, hn, hpts, o_np, o_st, o_err):
+            a.free()
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_s = 3 * args.cpu_sample_pairs  # ~10-30 s of CPU work on the box's cores
+        ci = np.arange(n_s) % nb
+        c_off = np.concatenate([[0], np.cumsum(np.diff(offs_b)[ci])]).astype(np.int32)
+        c_pts = np.concatenate([pts_b[offs_b[i]:offs_b[i + 1]] for i in ci])
+        c_prev, c_next = prev_b[ci], next_b[ci]
+        cpu_reference(c_prev, c_next, c_pts, c_off, min(8, n_s))
+        r = cpu_reference(c_prev, c_next, c_pts, c_off, n_s)
+        r1 = cpu_reference(c_prev, c_next, c_pts, c_off, min(n_s, 24), threads=1)
+        cpu = {"value": r["tracked"] / r["seconds"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": "%d pairs x %d corners (%.1f s), %s" % (r["pairs"], CORNERS, r["seconds"], r["what"]),
+               "single_thread_value": r1["tracked"] / r1["seconds"], "host_cpus": os.cpu_count()}
+        # parity of what was timed: GPU results vs the same CPU call on one pair
+        from oracle import cv2_ref
+        if cv2_ref.HAVE_CV2:
+            p_cv, s_cv, _ = cv2_ref.calc_optical_flow_pyr_lk(prev_b[0], next_b[0], pts_b[offs_b[0]:offs_b[1]], None, WIN, MAX_LEVEL, CRIT, FLAGS)
+            p_g = nxt_d[:offs[1]].cpu().numpy(); s_g = st_d[:offs[1]].cpu().numpy()
+            both = (s_cv == 1) & (s_g == 1)
+            d = np.linalg.norm(p_cv - p_g, axis=1)
+            cpu["parity_pair0"] = {"status_agree": float((s_cv == s_g).mean()), "frac_within_0.01px": float((d[both] <= 0.01).mean()),
+                                   "max_dpos": float(d[both].max())}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "int32 fixed-point windows + fp32 2x2 solve", "data": "synthetic", "config": dict(cfg, l2="inputs (%.1f GB/GPU/step) larger than L2" % ((2 * args.pairs * W_IMG * H_IMG) / 1e9)),
+               "submitted_features_per_s": feats_all * args.steps / (ms_total * 1e-3), "tracked_fraction": tracked_all / feats_all,
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        if e2e:
+            out["e2e"] = e2e
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

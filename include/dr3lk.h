@@ -53,6 +53,11 @@ int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream);
 int dr3lk_synchronize(dr3lk_ctx* ctx);
 /* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx);
+/* Kernel timing with CUDA events on the launching stream (bench.py's roofline leg).  While profiling is on, every
+ * LK launch and every pyramid build is bracketed by events; dr3lk_profile_read waits for them, returns the summed
+ * durations (milliseconds) and launch counts since the last read, and clears them. */
+int dr3lk_set_profiling(dr3lk_ctx* ctx, int on);
+int dr3lk_profile_read(dr3lk_ctx* ctx, float* lk_ms, int* lk_launches, float* pyramid_ms, int* pyramid_builds);
 /* Pinned host memory for callers that want the host-buffer entry points to overlap copies with compute. */
 void* dr3lk_host_alloc(size_t bytes);
 void dr3lk_host_free(void* p);

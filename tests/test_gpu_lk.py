@@ -115,17 +115,19 @@ def _torch_batch(ctx, dr3, prev, nxt, pts_list, **kw):
     offs = np.zeros(B + 1, np.int32)
     offs[1:] = np.cumsum([len(p) for p in pts_list])
     allp = np.concatenate(pts_list).astype(np.float32)
-    dp, dn = torch.from_numpy(prev).cuda(), torch.from_numpy(nxt).cuda()
-    dpts = torch.from_numpy(allp).cuda()
-    dnext = torch.zeros_like(dpts)
-    dst = torch.zeros(len(allp), dtype=torch.uint8, device="cuda")
-    derr = torch.zeros(len(allp), dtype=torch.float32, device="cuda")
-    dstats = torch.zeros(len(allp), dtype=torch.int32, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.track_batch(dp.data_ptr(), dn.data_ptr(), w, h, w, h * w, B, dpts.data_ptr(), dnext.data_ptr(), dst.data_ptr(),
-                    derr.data_ptr(), offs, dstats.data_ptr(), **kw)
-    ctx.synchronize()
-    ctx.set_stream(None)
+    stream = torch.cuda.Stream()  # torch and the library share one non-default stream
+    with torch.cuda.stream(stream):
+        dp, dn = torch.from_numpy(prev).cuda(), torch.from_numpy(nxt).cuda()
+        dpts = torch.from_numpy(allp).cuda()
+        dnext = torch.zeros_like(dpts)
+        dst = torch.zeros(len(allp), dtype=torch.uint8, device="cuda")
+        derr = torch.zeros(len(allp), dtype=torch.float32, device="cuda")
+        dstats = torch.zeros(len(allp), dtype=torch.int32, device="cuda")
+        ctx.set_stream(stream.cuda_stream)
+        ctx.track_batch(dp.data_ptr(), dn.data_ptr(), w, h, w, h * w, B, dpts.data_ptr(), dnext.data_ptr(), dst.data_ptr(),
+                        derr.data_ptr(), offs, dstats.data_ptr(), **kw)
+        ctx.synchronize()
+        ctx.set_stream(None)
     return dnext.cpu().numpy(), dst.cpu().numpy(), derr.cpu().numpy(), dstats.cpu().numpy().view(np.uint32), offs
 
 
