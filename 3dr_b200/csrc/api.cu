@@ -1,6 +1,7 @@
 // C ABI of dr3lk (include/dr3lk.h): context, device scratch management, parameter normalisation and the
 // orchestration of the pyramid + LK kernels.  Host code only; the kernels live in pyramid.cu / lk_*.cu.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -79,8 +80,12 @@ PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
 // Device scratch for one batch of frame pairs: Gaussian levels >= 1 of both frames, derivatives of the previous
 // frame at every level, optionally level-0 copies (host-buffer entry points), and the point arrays.
 struct Workspace {
-    DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs;
-    void release() { pyr_prev.release(); pyr_next.release(); deriv.release(); lvl0_prev.release(); lvl0_next.release(); pts.release(); offs.release(); }
+    DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs, pair_idx, al_prev, al_next, counter;
+    void release()
+    {
+        pyr_prev.release(); pyr_next.release(); deriv.release(); lvl0_prev.release(); lvl0_next.release(); pts.release();
+        offs.release(); pair_idx.release(); al_prev.release(); al_next.release(); counter.release();
+    }
 };
 
 struct LKArgs {
@@ -197,6 +202,8 @@ void fill_lk_scalars(LKParams& lk, const LKArgs& a)
     lk.max_count = (a.crit_type & DR3LK_TERM_COUNT) ? std::min(std::max(a.crit_max_count, 0), 100) : 30;
     double eps = (a.crit_type & DR3LK_TERM_EPS) ? std::min(std::max(a.crit_eps, 0.), 10.) : 0.01;
     lk.eps2 = eps * eps;
+    lk.eps2_lo = std::nextafterf((float)(lk.eps2 * (1.0 - 1e-6)), 0.f);
+    lk.eps2_hi = std::nextafterf((float)(lk.eps2 * (1.0 + 1e-6)), INFINITY);
     lk.min_eig_thr = a.min_eig_threshold;
     lk.win_w = a.win_w; lk.win_h = a.win_h;
     lk.flags = a.flags;
@@ -211,11 +218,11 @@ int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk)
     return DR3LK_OK;
 }
 
-// Device-resident batch on (W, stream).  pts_offset_dev: device copy of the offsets.
+// Device-resident batch on (W, stream).  pts_offset: host offsets, pts_offset_dev: device copy of the same.
 int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev_dev, const uint8_t* next_dev, int w,
                        int h, size_t pitch, size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev,
-                       uint8_t* status_dev, float* err_dev, const int* pts_offset_dev, int n_total, uint32_t* stats_dev,
-                       const LKArgs& a)
+                       uint8_t* status_dev, float* err_dev, const int* pts_offset, const int* pts_offset_dev, int n_total,
+                       uint32_t* stats_dev, const LKArgs& a)
 {
     LKParams lk;
     memset(&lk, 0, sizeof(lk));
@@ -224,6 +231,27 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     if (ctx->profiling) {
         for (int i = 0; i < 3; i++) CU_TRY(ctx, cudaEventCreate(&pr.e[i]));
         CU_TRY(ctx, cudaEventRecord(pr.e[0], stream));
+    }
+    // The specialised kernels stage image rows with 16-byte loads: give them a 16-B aligned level 0 when the
+    // caller's layout is not (e.g. continuous 1241-wide images).
+    const bool want_fast = lk_fast_supported(a.win_w, a.win_h);
+    auto aligned16 = [](const void* p, size_t a1, size_t a2) { return ((reinterpret_cast<uintptr_t>(p) | a1 | a2) & 15) == 0; };
+    if (want_fast && !(aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride))) {
+        const int ap = align_up(w, 16);
+        const size_t ab = (size_t)ap * h;
+        CU_TRY(ctx, W.al_prev.reserve(ab * batch));
+        CU_TRY(ctx, W.al_next.reserve(ab * batch));
+        if (image_stride == pitch * (size_t)h) {
+            CU_TRY(ctx, cudaMemcpy2DAsync(W.al_prev.p, ap, prev_dev, pitch, w, (size_t)h * batch, cudaMemcpyDeviceToDevice, stream));
+            CU_TRY(ctx, cudaMemcpy2DAsync(W.al_next.p, ap, next_dev, pitch, w, (size_t)h * batch, cudaMemcpyDeviceToDevice, stream));
+        } else {
+            for (int b = 0; b < batch; b++) {
+                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.al_prev.p + ab * b, ap, prev_dev + image_stride * b, pitch, w, h, cudaMemcpyDeviceToDevice, stream));
+                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.al_next.p + ab * b, ap, next_dev + image_stride * b, pitch, w, h, cudaMemcpyDeviceToDevice, stream));
+            }
+        }
+        prev_dev = (const uint8_t*)W.al_prev.p; next_dev = (const uint8_t*)W.al_next.p;
+        pitch = ap; image_stride = ab;
     }
     int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, (int)pitch, image_stride, batch, P, lk);
     if (rc != DR3LK_OK) return rc;
@@ -234,9 +262,24 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     lk.status = status_dev;
     lk.err = err_dev;
     lk.stats = stats_dev;
-    lk.pts_offset = pts_offset_dev;
     lk.batch = batch;
     lk.n_total = n_total;
+    lk.fast_ok = aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride);
+    CU_TRY(ctx, W.counter.reserve(sizeof(int)));
+    lk.work_counter = (int*)W.counter.p;
+    // point -> pair mapping: a division when every pair has the same number of points, else a lookup table
+    bool uniform = n_total % batch == 0;
+    for (int b = 0; uniform && b < batch; b++) uniform = (pts_offset[b + 1] - pts_offset[b]) == n_total / batch;
+    if (uniform) {
+        lk.uniform_n = n_total / batch;
+    } else {
+        CU_TRY(ctx, W.pair_idx.reserve(sizeof(int) * (size_t)n_total));
+        Launch L{stream, cudaSuccess, 0};
+        launch_pair_index(L, pts_offset_dev, batch, n_total, (int*)W.pair_idx.p);
+        ctx->launches += L.launches;
+        if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pair index kernel launch");
+        lk.pair_idx = (const int*)W.pair_idx.p;
+    }
     rc = run_lk(ctx, stream, lk);
     if (ctx->profiling) {
         CU_TRY(ctx, cudaEventRecord(pr.e[2], stream));
@@ -500,7 +543,7 @@ int dr3lk_track_batch(dr3lk_ctx* ctx, const uint8_t* prev_dev, const uint8_t* ne
     CU_TRY(ctx, ctx->ws.offs.reserve(sizeof(int) * (size_t)(batch + 1)));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->ws.offs.p, pts_offset, sizeof(int) * (size_t)(batch + 1), cudaMemcpyHostToDevice, ctx->stream));
     return track_batch_device(ctx, ctx->ws, ctx->stream, prev_dev, next_dev, w, h, pitch, image_stride, batch, prev_pts_dev,
-                              next_pts_dev, status_dev, err_dev, (const int*)ctx->ws.offs.p, n_total, stats_dev, a);
+                              next_pts_dev, status_dev, err_dev, pts_offset, (const int*)ctx->ws.offs.p, n_total, stats_dev, a);
 }
 
 int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t prev_step, const uint8_t* next, size_t next_step,
@@ -538,7 +581,7 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
     rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, 1,
                             (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
-                            (const int*)W.offs.p, n, nullptr, a);
+                            offs, (const int*)W.offs.p, n, nullptr, a);
     if (rc != DR3LK_OK) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(next_pts, dp + o_next, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaMemcpyAsync(status, dp + o_status, (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -622,7 +665,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs_host.data() + offs_pos[c], sizeof(int) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
         rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, nb,
                                 (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
-                                (const int*)W.offs.p, n, stats ? (uint32_t*)(dp + o_stats) : nullptr, a);
+                                offs_host.data() + offs_pos[c], (const int*)W.offs.p, n, stats ? (uint32_t*)(dp + o_stats) : nullptr, a);
         if (rc != DR3LK_OK) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(next_pts + 2 * (size_t)p0, dp + o_next, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaMemcpyAsync(status + p0, dp + o_status, (size_t)n, cudaMemcpyDeviceToHost, st));

@@ -30,7 +30,11 @@ struct LKParams {
     uint8_t* status;
     float* err;            // may be null
     uint32_t* stats;       // may be null
-    const int* pts_offset; // device, batch+1 entries
+    const int* pair_idx;   // device, one frame-pair index per point (used when uniform_n == 0)
+    int uniform_n;         // > 0: every pair has exactly this many points (pair = point / uniform_n)
+    int fast_ok;           // all level images / derivatives are 16-B aligned (base, pitch, stride)
+    int* work_counter;     // device int, zeroed by the launcher: next point index for the persistent warps
+    float eps2_lo, eps2_hi; // fp32 brackets of eps2: below lo / above hi the fp32 estimate of |delta|^2 decides
     double eps2;           // criteria.epsilon^2
     double min_eig_thr;
     int batch;
@@ -58,8 +62,10 @@ void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_
 
 // lk_generic.cu
 void launch_lk_generic(Launch& L, const LKParams& p);
+void launch_pair_index(Launch& L, const int* pts_offset_dev, int batch, int n_total, int* pair_idx_dev);
 // lk_fast.cu -- returns false when the window size has no specialised kernel
 bool launch_lk_fast(Launch& L, const LKParams& p);
+bool lk_fast_supported(int win_w, int win_h);
 
 // ---- device helpers ----
 __device__ __forceinline__ int reflect101(int p, int len)

@@ -1,13 +1,540 @@
-// Specialised LK kernels (compile-time window sizes).  Placeholder until the tuned kernels land:
-// every window size currently goes through lk_generic.cu.
+// Specialised pyramidal-LK tracker kernels (compile-time window sizes) for sm_100a -- warp per feature, all levels
+// in one launch.  Same arithmetic as lk_generic.cu / OpenCV's LKTrackerInvoker (reference call
+// site src/initialization.cpp:608-613), bit-identical results, but organised for the SM:
+//
+//   * Per level the warp stages three regions in shared memory with 16-byte row-coalesced loads (every image row of
+//     the window is touched once per level): the template window of the previous image (u8), its Scharr derivatives
+//     (packed s16x2) and a search region of the next image (window + >= 13 px margin in x, 8 px in y).  Borders are
+//     resolved while staging (REFLECT_101 index reflection for images, zeros for derivatives), so the compute code
+//     never branches on borders.  The search region is re-staged only when the window leaves it.
+//   * The window is cut into runs of R consecutive pixels of one row; each lane owns NRUN runs.  A run's R+1 source
+//     bytes of two rows are fetched as 3-4 aligned 32-bit shared loads and realigned with PRMT, and the 14-bit
+//     bilinear blend is two IDP.2A (dp2a: 2 x (s16 weight * u8 pixel)) per pixel instead of four IMADs.
+//   * The template (Ix, Iy per pixel) lives in registers for the whole level.  sum((J - I) * Ix) is evaluated as
+//     sum(J * Ix) - sum(I * Ix): the second term is constant per level, so an iteration costs 2 IDP + 1 shift +
+//     2 IMAD per pixel.  All sums are exact integers: per-lane int32 partials, warp totals through REDUX on the
+//     16-bit halves, one rounding to fp32 -- results do not depend on summation order.
+//   * Scalar fp32 steps use explicitly rounded intrinsics (no FMA contraction) and match the CPU oracle bit for bit.
+#include <float.h>
+
+#include <algorithm>
+
 #include "dr3lk_internal.cuh"
 
 namespace dr3lk {
 
+namespace {
+
+
+constexpr int pitch_words_for(int need)  // smallest p >= need with p % 8 == 4: 16-B aligned rows, rows 4 banks apart
+{
+    int p = need;
+    while (p % 8 != 4) p++;
+    return p;
+}
+
+template <int WW_, int WH_, int R_>
+struct Geo {
+    static constexpr int WW = WW_, WH = WH_, R = R_;
+    static constexpr int NCB = (WW + R - 1) / R;         // runs per window row
+    static constexpr int NRUNS = NCB * WH;
+    static constexpr int NRUN = (NRUNS + 31) / 32;       // runs per lane
+    static constexpr int NWD = (R + 1 + 3 + 3) / 4;      // 32-bit words covering R+1 bytes at any byte alignment
+    static constexpr int NEO = (R + 3) / 4;              // realigned registers per parity
+    static constexpr bool RAGGED = (WW % R) != 0;
+    static constexpr int WARPS = 4;                      // warps per CTA (each warp is an independent worker)
+    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? 4 : 2;  // register budget: 128 / thread, or 255 for big windows
+    static constexpr int MX = 13, MY = 8;                // search-region margins (x margin is >= MX after alignment)
+    static constexpr int J_CH = (WW + 1 + 2 * MX + 15 + 15) / 16;  // 16-B chunks per search-region row
+    static constexpr int J_W = J_CH * 16;
+    static constexpr int J_H = WH + 1 + 2 * MY;
+    static constexpr int J_PW = pitch_words_for(J_CH * 4);
+    static constexpr int I_CH = (WW + 1 + 15 + 15) / 16;
+    static constexpr int I_W = I_CH * 16;
+    static constexpr int I_PW = pitch_words_for(I_CH * 4);
+    static constexpr int D_CH = (WW + 1 + 3 + 3) / 4;    // chunks of 4 derivative words
+    static constexpr int D_PW = pitch_words_for(D_CH * 4);
+    static constexpr int J_WORDS = J_PW * J_H + 4;       // +4: realignment may read one word past the last row
+    static constexpr int I_WORDS = I_PW * (WH + 1) + 4;
+    static constexpr int D_ZERO = D_PW * (WH + 1);       // two rows of zeros for runs that do not exist
+    static constexpr int D_WORDS = D_PW * (WH + 3) + 4;
+    // smallest level the kernel accepts: one reflection must suffice for every row / column staging can touch
+    static constexpr int MIN_H = WH + MY + 2;
+    static constexpr int MIN_W = (J_W > I_W ? J_W : I_W) + 1;
+    static constexpr int WARP_WORDS = (J_WORDS + I_WORDS + D_WORDS + 3) / 4 * 4;
+    static_assert((long long)NRUN * R * 8160LL * 4080LL < 2147483647LL, "per-lane int32 partial sums would overflow");
+    static_assert(J_W >= WW + 1 + MX + MX + 15, "search region too narrow");
+};
+
+__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// exact warp total of per-lane int32 partials, as (hi, lo) with total = hi * 65536 + lo
+struct HiLo {
+    int hi, lo;
+};
+__device__ __forceinline__ HiLo warp_sum_hilo(int v)
+{
+    HiLo r;
+    r.lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    r.hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return r;
+}
+// rn_fp32(hi * 65536 + lo): both conversions are exact (|hi| < 2^24, |lo| < 2^24), the fma rounds once
+__device__ __forceinline__ float hilo_to_float(int hi, int lo) { return __fmaf_rn((float)hi, 65536.f, (float)lo); }
+
+struct Weights {
+    int w00, w01, w10, w11;
+    int wt, wb;  // (w00 | w01 << 16), (w10 | w11 << 16) for dp2a
+};
+__device__ __forceinline__ Weights make_weights(float a, float b)
+{
+    Weights q;
+    const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
+    q.w00 = __float2int_rn(__fmul_rn(__fmul_rn(oma, omb), 16384.f));
+    q.w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, omb), 16384.f));
+    q.w10 = __float2int_rn(__fmul_rn(__fmul_rn(oma, b), 16384.f));
+    q.w11 = (1 << W_BITS) - q.w00 - q.w01 - q.w10;
+    q.wt = (q.w00 & 0xffff) | (q.w01 << 16);
+    q.wb = (q.w10 & 0xffff) | (q.w11 << 16);
+    return q;
+}
+
+// R+1 consecutive bytes of two shared-memory rows (byte offset `boff` in a region of `PW` words per row), realigned so
+// that pixel k's (p[k], p[k+1]) pair sits in the low or high half of a register: even k -> E[k/4], odd k -> O[k/4],
+// high half when (k & 2).
+template <int R, int NWD, int NEO, int PW>
+struct RunBytes {
+    unsigned tE[NEO], tO[NEO], bE[NEO], bO[NEO];
+    __device__ __forceinline__ void load(const unsigned* __restrict__ region, int boff)
+    {
+        const unsigned* p = region + (boff >> 2);
+        const unsigned o = boff & 3;
+        const unsigned selE = 0x3210u + o * 0x1111u, selO = selE + 0x1111u;
+        unsigned t[NWD], b[NWD];
+#pragma unroll
+        for (int i = 0; i < NWD; i++) { t[i] = p[i]; b[i] = p[PW + i]; }
+#pragma unroll
+        for (int j = 0; j < NEO; j++) {
+            tE[j] = __byte_perm(t[j], t[j + 1 < NWD ? j + 1 : j], selE);
+            bE[j] = __byte_perm(b[j], b[j + 1 < NWD ? j + 1 : j], selE);
+            tO[j] = __byte_perm(t[j], t[j + 1 < NWD ? j + 1 : j], selO);
+            bO[j] = __byte_perm(b[j], b[j + 1 < NWD ? j + 1 : j], selO);
+        }
+    }
+    // (S + 2^8) >> 9 for pixel k of the run
+    __device__ __forceinline__ int sample(int k, const Weights& q) const
+    {
+        const unsigned tt = (k & 1) ? tO[k >> 2] : tE[k >> 2];
+        const unsigned bb = (k & 1) ? bO[k >> 2] : bE[k >> 2];
+        int s;
+        if (k & 2) { s = dp2a_hi(q.wt, tt, 1 << (W_BITS - 5 - 1)); s = dp2a_hi(q.wb, bb, s); }
+        else { s = dp2a_lo(q.wt, tt, 1 << (W_BITS - 5 - 1)); s = dp2a_lo(q.wb, bb, s); }
+        return s >> (W_BITS - 5);
+    }
+};
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// REFLECT_101 for -(len-1) <= p <= 2*len-2 (one reflection).  launch_lk_fast only takes levels large enough that
+// every row/column the staging code touches is in that range (Geo::MIN_W / MIN_H); smaller images use lk_generic.
+__device__ __forceinline__ int reflect_once(int p, int len)
+{
+    const int a = abs(p);
+    return min(a, 2 * len - 2 - a);
+}
+
+__host__ __device__ constexpr int pow2_at_least(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
+
+template <typename G>
+struct Tracker {
+    static constexpr int WW = G::WW, WH = G::WH;
+
+    // Rows of 16-byte chunks, LPR (power of two) lanes per row: global -> shared with 128-bit loads/stores.
+    // row_ptr(row) returns the global address of the row's first chunk, or nullptr for a row of zeros.
+    template <int NROWS, int CH, int PITCH_BYTES, typename RowPtr>
+    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, RowPtr row_ptr)
+    {
+        constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = (NROWS + RPR - 1) / RPR;
+        const int ch = lane & (LPR - 1), rr = lane / LPR;
+#pragma unroll
+        for (int i = 0; i < ROUNDS; i++) {
+            const int row = rr + i * RPR;
+            if (row < NROWS && ch < CH) {
+                const uint8_t* src = row_ptr(row);
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (src) v = ldg128(src + ch * 16);
+                *reinterpret_cast<uint4*>(sb + row * PITCH_BYTES + ch * 16) = v;
+            }
+        }
+    }
+
+    // ---- staging -------------------------------------------------------------------------------------------
+    // Search region of the next image around window origin (inx, iny).  Sets rx0/ry0 and the valid x range.
+    static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int w, int h, int inx,
+                                                   int iny, int lane, int& rx0, int& ry0, int& vspan)
+    {
+        ry0 = iny - G::MY;
+        uint8_t* sb = reinterpret_cast<uint8_t*>(sJ);
+        if (inx >= 0 && inx + WW < w) {
+            int x0 = (inx - G::MX) & ~15;
+            x0 = max(0, min(x0, pitch - G::J_W));
+            rx0 = x0;
+            vspan = min(x0 + G::J_W, w) - x0 - (WW + 1);  // window origins rx0 .. rx0 + vspan are inside the region
+            const int y0 = ry0;
+            stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sb, lane, [&](int row) {
+                return img + (long long)reflect_once(y0 + row, h) * pitch + x0;
+            });
+        } else {
+            // window touches the left/right border: byte-wise with reflection in x and y
+            rx0 = inx - (G::J_W - (WW + 1)) / 2;
+            vspan = G::J_W - (WW + 1);
+            int gx[(G::J_W + 31) / 32];
+#pragma unroll
+            for (int c = 0; c < (G::J_W + 31) / 32; c++) gx[c] = reflect_once(rx0 + lane + 32 * c, w);
+#pragma unroll 2
+            for (int row = 0; row < G::J_H; row++) {
+                const uint8_t* src = img + (long long)reflect_once(ry0 + row, h) * pitch;
+#pragma unroll
+                for (int c = 0; c < (G::J_W + 31) / 32; c++)
+                    if (lane + 32 * c < G::J_W) sb[row * (G::J_PW * 4) + lane + 32 * c] = __ldg(src + gx[c]);
+            }
+        }
+        __syncwarp();
+    }
+
+    // Template window of the previous image: WH+1 rows from ipy, bytes from x0 (returned) .. x0 + I_W
+    static __device__ __forceinline__ int stage_I(unsigned* sI, const uint8_t* __restrict__ img, int pitch, int w, int h, int ipx, int ipy,
+                                                  int lane)
+    {
+        uint8_t* sb = reinterpret_cast<uint8_t*>(sI);
+        int x0;
+        if (ipx >= 0 && ipx + WW < w) {
+            x0 = min(ipx & ~15, pitch - G::I_W);
+            stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sb, lane, [&](int row) {
+                return img + (long long)reflect_once(ipy + row, h) * pitch + x0;
+            });
+        } else {
+            x0 = ipx;
+            int gx[(G::I_W + 31) / 32];
+#pragma unroll
+            for (int c = 0; c < (G::I_W + 31) / 32; c++) gx[c] = reflect_once(x0 + lane + 32 * c, w);
+#pragma unroll 2
+            for (int row = 0; row <= WH; row++) {
+                const uint8_t* src = img + (long long)reflect_once(ipy + row, h) * pitch;
+#pragma unroll
+                for (int c = 0; c < (G::I_W + 31) / 32; c++)
+                    if (lane + 32 * c < G::I_W) sb[row * (G::I_PW * 4) + lane + 32 * c] = __ldg(src + gx[c]);
+            }
+        }
+        return x0;
+    }
+
+    // Scharr derivatives of the template window (zero outside the image): WH+1 rows, words from x0 (returned)
+    static __device__ __forceinline__ int stage_D(unsigned* sD, const int* __restrict__ der, int dpitch, int w, int h, int ipx, int ipy,
+                                                  int lane)
+    {
+        int x0;
+        if (ipx >= 0 && ipx + WW < w) {
+            x0 = min(ipx & ~3, dpitch - G::D_CH * 4);
+            stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(reinterpret_cast<uint8_t*>(sD), lane, [&](int row) -> const uint8_t* {
+                const int gy = ipy + row;
+                if ((unsigned)gy >= (unsigned)h) return nullptr;
+                return reinterpret_cast<const uint8_t*>(der + (long long)gy * dpitch + x0);
+            });
+        } else {
+            x0 = ipx;
+#pragma unroll 2
+            for (int row = 0; row <= WH; row++) {
+                const int gy = ipy + row;
+                const bool yin = (unsigned)gy < (unsigned)h;
+                if (lane < G::D_CH * 4) {
+                    const int gx = x0 + lane;
+                    unsigned v = 0;
+                    if (yin && (unsigned)gx < (unsigned)w) v = (unsigned)__ldg(der + (long long)gy * dpitch + gx);
+                    sD[row * G::D_PW + lane] = v;
+                }
+            }
+        }
+        return x0;
+    }
+};
+
+// Persistent warps: every warp pulls the next feature index from a global counter until the batch is exhausted, so a
+// slow feature (many iterations) never holds other warps' slots.
+template <typename G>
+__global__ void __launch_bounds__(G::WARPS * 32, G::MIN_BLOCKS)
+lk_fast_kernel(const __grid_constant__ LKParams P)
+{
+    constexpr int WW = G::WW, WH = G::WH, R = G::R, NRUN = G::NRUN;
+    using T = Tracker<G>;
+    extern __shared__ __align__(16) unsigned smem_u[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned* sJ = smem_u + warp * G::WARP_WORDS;
+    unsigned* sI = sJ + G::J_WORDS;
+    unsigned* sD = sI + G::I_WORDS;
+
+    // ---- run geometry of this lane (constant for the whole kernel) ----
+    int jofs[NRUN], iofs[NRUN], dofs[NRUN];
+    bool rvalid[NRUN], rlast[NRUN];
+#pragma unroll
+    for (int s = 0; s < NRUN; s++) {
+        const int q = lane + 32 * s;
+        rvalid[s] = q < G::NRUNS;
+        const int r = rvalid[s] ? q / G::NCB : 0, c = rvalid[s] ? q - r * G::NCB : 0;
+        rlast[s] = c == G::NCB - 1;
+        jofs[s] = r * (G::J_PW * 4) + c * R;
+        iofs[s] = r * (G::I_PW * 4) + c * R;
+        // runs that do not exist read two rows of zeros (kept behind the derivative region): their Ix = Iy = 0
+        dofs[s] = rvalid[s] ? r * G::D_PW + c * R : G::D_ZERO;
+    }
+    if (lane < 2 * (R + 1)) sD[G::D_ZERO + (lane / (R + 1)) * G::D_PW + lane % (R + 1)] = 0;
+    __syncwarp();
+
+    constexpr float hwx = (WW - 1) * 0.5f, hwy = (WH - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const bool want_err = P.err != nullptr;
+    const bool get_min_eig = (P.flags & DR3LK_GET_MIN_EIGENVALS) != 0;
+
+    for (;;) {
+        int f = 0;
+        if (lane == 0) f = atomicAdd(P.work_counter, 1);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= P.n_total) break;
+
+        const int pair = P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f);
+        const float2 pp = P.prev_pts[f];
+        float2 np = make_float2(0.f, 0.f);
+        if (P.flags & DR3LK_USE_INITIAL_FLOW) np = P.next_pts[f];
+
+        int status = 1;
+        float err = 0.f;
+        unsigned n_iters = 0, n_templates = 0, err_pass = 0;
+
+        for (int level = P.max_level; level >= 0; --level) {
+            const LevelDesc& L = P.lv[level];
+            const int w = L.w, h = L.h;
+            const float sc = __int_as_float((127 - level) << 23);
+
+            float px = __fmul_rn(pp.x, sc), py = __fmul_rn(pp.y, sc);
+            float nx, ny;
+            if (level == P.max_level) {
+                if (P.flags & DR3LK_USE_INITIAL_FLOW) { nx = __fmul_rn(np.x, sc); ny = __fmul_rn(np.y, sc); }
+                else { nx = px; ny = py; }
+            } else {
+                nx = __fmul_rn(np.x, 2.f); ny = __fmul_rn(np.y, 2.f);
+            }
+            np.x = nx; np.y = ny;
+
+            px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
+            const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+            if ((unsigned)(ipx + WW) >= (unsigned)(w + WW) || (unsigned)(ipy + WH) >= (unsigned)(h + WH)) {
+                if (level == 0) { status = 0; err = 0.f; }
+                continue;
+            }
+            Weights q = make_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
+
+            // ---- template: stage I and derivative windows, build (I, Ix, Iy) in registers, Gram matrix ----
+            n_templates++;
+            const uint8_t* imgI = L.prev + (long long)pair * L.prev_stride;
+            const int* der = L.deriv + (long long)pair * L.deriv_stride;
+            __syncwarp();
+            const int ix0 = T::stage_I(sI, imgI, L.pitch_p, w, h, ipx, ipy, lane);
+            const int dx0 = T::stage_D(sD, der, L.dpitch, w, h, ipx, ipy, lane);
+            __syncwarp();
+            const int ox = ipx - ix0, oxw = ipx - dx0;
+
+            int dxr[NRUN][R], dyr[NRUN][R];
+            unsigned i5p[NRUN][(R + 1) / 2];
+            int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+            for (int s = 0; s < NRUN; s++) {
+                RunBytes<R, G::NWD, G::NEO, G::I_PW> rb;
+                rb.load(sI, iofs[s] + ox);
+                const unsigned* dp = sD + dofs[s] + (rvalid[s] ? oxw : 0);
+                int tx[R + 1], ty[R + 1], bx[R + 1], by[R + 1];
+#pragma unroll
+                for (int k = 0; k <= R; k++) {
+                    const int dt = (int)dp[k], db = (int)dp[G::D_PW + k];
+                    tx[k] = (short)dt; ty[k] = dt >> 16;
+                    bx[k] = (short)db; by[k] = db >> 16;
+                }
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    const int i5 = rb.sample(k, q);
+                    int ix = (tx[k] * q.w00 + tx[k + 1] * q.w01 + bx[k] * q.w10 + bx[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    int iy = (ty[k] * q.w00 + ty[k + 1] * q.w01 + by[k] * q.w10 + by[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    if (G::RAGGED && k >= WW - (G::NCB - 1) * R && rlast[s]) { ix = 0; iy = 0; }  // pixels past the window edge
+                    dxr[s][k] = ix; dyr[s][k] = iy;
+                    if (k & 1) i5p[s][k >> 1] |= (unsigned)i5 << 16; else i5p[s][k >> 1] = (unsigned)i5;
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                    c1 += i5 * ix; c2 += i5 * iy;
+                }
+            }
+            const HiLo s11 = warp_sum_hilo(a11), s12 = warp_sum_hilo(a12), s22 = warp_sum_hilo(a22);
+            const HiLo sc1 = warp_sum_hilo(c1), sc2 = warp_sum_hilo(c2);
+            // normalise the constants sum(I*Ix), sum(I*Iy) to hi * 65536 + lo with 0 <= lo < 65536
+            const int c1hi = sc1.hi + (sc1.lo >> 16), c1lo = sc1.lo & 0xffff;
+            const int c2hi = sc2.hi + (sc2.lo >> 16), c2lo = sc2.lo & 0xffff;
+
+            const float A11 = __fmul_rn(hilo_to_float(s11.hi, s11.lo), FLT_SCALE);
+            const float A12 = __fmul_rn(hilo_to_float(s12.hi, s12.lo), FLT_SCALE);
+            const float A22 = __fmul_rn(hilo_to_float(s22.hi, s22.lo), FLT_SCALE);
+            float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+            const float dA = __fsub_rn(A11, A22);
+            const float rad = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+            const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WW * WH));
+            if (want_err && get_min_eig) err = minEig;
+            if ((double)minEig < P.min_eig_thr || D < FLT_EPSILON) {
+                if (level == 0) status = 0;
+                continue;
+            }
+            D = __fdiv_rn(1.f, D);
+
+            // ---- iterations ----
+            const uint8_t* imgJ = L.next + (long long)pair * L.next_stride;
+            nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+            float pdx = 0.f, pdy = 0.f;
+            int rx0 = 0, ry0 = 0, vspan = 0;
+            bool staged = false, moved = false;
+            for (int j = 0; j < P.max_count; ++j) {
+                const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+                if ((unsigned)(inx + WW) >= (unsigned)(w + WW) || (unsigned)(iny + WH) >= (unsigned)(h + WH)) {
+                    if (level == 0) status = 0;
+                    break;
+                }
+                q = make_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
+                if (!staged || (unsigned)(inx - rx0) > (unsigned)vspan || (unsigned)(iny - ry0) > (unsigned)(2 * G::MY)) {
+                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, inx, iny, lane, rx0, ry0, vspan);
+                    staged = true;
+                }
+                const int jbase = (iny - ry0) * (G::J_PW * 4) + (inx - rx0);
+                int b1 = 0, b2 = 0;
+#pragma unroll
+                for (int s = 0; s < NRUN; s++) {
+                    RunBytes<R, G::NWD, G::NEO, G::J_PW> rb;
+                    rb.load(sJ, jbase + jofs[s]);
+#pragma unroll
+                    for (int k = 0; k < R; k++) {
+                        const int j5 = rb.sample(k, q);
+                        b1 += j5 * dxr[s][k];
+                        b2 += j5 * dyr[s][k];
+                    }
+                }
+                const HiLo sb1 = warp_sum_hilo(b1), sb2 = warp_sum_hilo(b2);
+                n_iters++;
+                // sum((J - I) * Ix) = sum(J * Ix) - sum(I * Ix), exact; one rounding to fp32
+                const float fb1 = __fmul_rn(hilo_to_float(sb1.hi - c1hi, sb1.lo - c1lo), FLT_SCALE);
+                const float fb2 = __fmul_rn(hilo_to_float(sb2.hi - c2hi, sb2.lo - c2lo), FLT_SCALE);
+                const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+                const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+                nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
+                moved = true;
+                // |delta|^2 <= eps^2 in double like OpenCV; the fp32 estimate decides unless it is within 1e-6 of the threshold
+                const float t = __fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
+                bool conv = t < P.eps2_lo;
+                if (!conv && !(t > P.eps2_hi))
+                    conv = __dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)) <= P.eps2;
+                if (conv) break;
+                // fabs(float) < 0.01 (double)  <=>  fabs(float) <= 0.01f, because 0.01f is the largest float below 0.01
+                if (j > 0 && fabsf(__fadd_rn(ddx, pdx)) <= 0.01f && fabsf(__fadd_rn(ddy, pdy)) <= 0.01f) {
+                    np.x = __fsub_rn(__fadd_rn(nx, hwx), __fmul_rn(ddx, 0.5f));
+                    np.y = __fsub_rn(__fadd_rn(ny, hwy), __fmul_rn(ddy, 0.5f));
+                    moved = false;
+                    break;
+                }
+                pdx = ddx; pdy = ddy;
+            }
+            if (moved) { np.x = __fadd_rn(nx, hwx); np.y = __fadd_rn(ny, hwy); }
+
+            if (status && want_err && level == 0 && !get_min_eig) {
+                const float qx = __fsub_rn(np.x, hwx), qy = __fsub_rn(np.y, hwy);
+                const int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
+                if ((unsigned)(iqx + WW) >= (unsigned)(w + WW) || (unsigned)(iqy + WH) >= (unsigned)(h + WH)) {
+                    status = 0;
+                    continue;
+                }
+                q = make_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy));
+                if (!staged || (unsigned)(iqx - rx0) > (unsigned)vspan || (unsigned)(iqy - ry0) > (unsigned)(2 * G::MY))
+                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, iqx, iqy, lane, rx0, ry0, vspan);
+                const int jbase = (iqy - ry0) * (G::J_PW * 4) + (iqx - rx0);
+                int es = 0;
+#pragma unroll
+                for (int s = 0; s < NRUN; s++) {
+                    RunBytes<R, G::NWD, G::NEO, G::J_PW> rb;
+                    rb.load(sJ, jbase + jofs[s]);
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < R; k++) {
+                        const int i5 = (k & 1) ? (int)(i5p[s][k >> 1] >> 16) : (int)(i5p[s][k >> 1] & 0xffffu);
+                        const int d = abs(rb.sample(k, q) - i5);
+                        if (G::RAGGED && k >= WW - (G::NCB - 1) * R) e += rlast[s] ? 0 : d; else e += d;
+                    }
+                    es += rvalid[s] ? e : 0;
+                }
+                es = __reduce_add_sync(0xffffffffu, es);
+                err_pass = 1;
+                err = __fdiv_rn(__fmul_rn((float)es, 1.f), (float)(32 * WW * WH));
+            }
+        }
+
+        if (lane == 0) {
+            P.next_pts[f] = np;
+            P.status[f] = (uint8_t)status;
+            if (want_err) P.err[f] = err;
+            if (P.stats) P.stats[f] = (n_iters & 0xffffu) | ((n_templates & 0xffu) << 16) | (err_pass << 24);
+        }
+    }
+}
+
+template <typename G>
+bool launch_one(Launch& L, const LKParams& p)
+{
+    for (int l = 0; l <= p.max_level; l++)
+        if (p.lv[l].w < G::MIN_W || p.lv[l].h < G::MIN_H) return false;  // tiny level: lk_generic handles it
+    const size_t smem = (size_t)G::WARPS * G::WARP_WORDS * sizeof(unsigned);
+    L.err = cudaFuncSetAttribute(lk_fast_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (L.err != cudaSuccess) return true;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_fast_kernel<G>, G::WARPS * 32, smem);
+    if (L.err != cudaSuccess) return true;
+    const int want = (p.n_total + G::WARPS - 1) / G::WARPS;
+    const int blocks = std::min(want, std::max(1, per_sm) * sms);
+    L.err = cudaMemsetAsync(p.work_counter, 0, sizeof(int), L.stream);
+    if (L.err != cudaSuccess) return true;
+    lk_fast_kernel<G><<<blocks, G::WARPS * 32, smem, L.stream>>>(p);
+    L.err = cudaGetLastError();
+    L.launches++;
+    return true;
+}
+
+}  // namespace
+
+bool lk_fast_supported(int win_w, int win_h)
+{
+    return (win_w == 21 && win_h == 21) || (win_w == 31 && win_h == 31) || (win_w == 30 && win_h == 30);
+}
+
 bool launch_lk_fast(Launch& L, const LKParams& p)
 {
-    (void)L; (void)p;
-    return false;
+    if (!lk_fast_supported(p.win_w, p.win_h) || !p.fast_ok) return false;
+    if (L.err != cudaSuccess || p.n_total <= 0) return true;
+    if (p.win_w == 21) return launch_one<Geo<21, 21, 7>>(L, p);
+    if (p.win_w == 31) return launch_one<Geo<31, 31, 8>>(L, p);
+    return launch_one<Geo<30, 30, 10>>(L, p);
 }
 
 }  // namespace dr3lk

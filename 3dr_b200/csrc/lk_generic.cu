@@ -83,15 +83,7 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
     short* s_I = reinterpret_cast<short*>(s_dxdy + npix);
 
     // which frame pair does this feature belong to?
-    int pair = 0;
-    {
-        int lo = 0, hi = P.batch;  // find pair with pts_offset[pair] <= f < pts_offset[pair+1]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(P.pts_offset + mid) <= f) lo = mid; else hi = mid;
-        }
-        pair = lo;
-    }
+    const int pair = P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f);
 
     const float2 pp = P.prev_pts[f];
     float2 np = make_float2(0.f, 0.f);
@@ -237,6 +229,27 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
 }
 
 }  // namespace
+
+// pair index of every point: binary search in the offsets (only for ragged batches)
+__global__ void pair_index_kernel(const int* __restrict__ offs, int batch, int n_total, int* __restrict__ pair_idx)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_total) return;
+    int lo = 0, hi = batch;  // offs[lo] <= f < offs[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offs + mid) <= f) lo = mid; else hi = mid;
+    }
+    pair_idx[f] = lo;
+}
+
+void launch_pair_index(Launch& L, const int* pts_offset_dev, int batch, int n_total, int* pair_idx_dev)
+{
+    if (L.err != cudaSuccess || n_total <= 0) return;
+    pair_index_kernel<<<(n_total + 255) / 256, 256, 0, L.stream>>>(pts_offset_dev, batch, n_total, pair_idx_dev);
+    L.err = cudaGetLastError();
+    L.launches++;
+}
 
 size_t lk_generic_smem_bytes(int win_w, int win_h)
 {
