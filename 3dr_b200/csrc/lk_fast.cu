@@ -146,6 +146,10 @@ struct RunBytes {
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // REFLECT_101 for -(len-1) <= p <= 2*len-2 (one reflection).  launch_lk_fast only takes levels large enough that
 // every row/column the staging code touches is in that range (Geo::MIN_W / MIN_H); smaller images use lk_generic.
 __device__ __forceinline__ int reflect_once(int p, int len)
@@ -160,26 +164,31 @@ template <typename G>
 struct Tracker {
     static constexpr int WW = G::WW, WH = G::WH;
 
-    // Rows of 16-byte chunks, LPR (power of two) lanes per row: global -> shared with 128-bit loads/stores.
-    // row_ptr(row) returns the global address of the row's first chunk, or nullptr for a row of zeros.
+    // Rows of 16-byte chunks, LPR (power of two) lanes per row: global -> shared with cp.async (LDGSTS, no registers,
+    // completion tracked per commit group).  row_ptr(row) returns the global address of the row's first chunk, or
+    // nullptr for a row of zeros (src-size 0 zero-fills).
     template <int NROWS, int CH, int PITCH_BYTES, typename RowPtr>
-    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, RowPtr row_ptr)
+    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, const void* any_valid_global, RowPtr row_ptr)
     {
         constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = (NROWS + RPR - 1) / RPR;
         const int ch = lane & (LPR - 1), rr = lane / LPR;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sb) + rr * PITCH_BYTES + ch * 16;
 #pragma unroll
         for (int i = 0; i < ROUNDS; i++) {
             const int row = rr + i * RPR;
             if (row < NROWS && ch < CH) {
                 const uint8_t* src = row_ptr(row);
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (src) v = ldg128(src + ch * 16);
-                *reinterpret_cast<uint4*>(sb + row * PITCH_BYTES + ch * 16) = v;
+                const int nbytes = src ? 16 : 0;
+                const void* g = src ? (const void*)(src + ch * 16) : any_valid_global;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g), "r"(nbytes)
+                             : "memory");
             }
         }
     }
 
     // ---- staging -------------------------------------------------------------------------------------------
+    // All stage_* functions only ISSUE the copies (cp.async, or plain stores on the rare byte-wise border path); the
+    // caller commits the group, waits for it and __syncwarp()s before any lane reads the region.
     // Search region of the next image around window origin (inx, iny).  Sets rx0/ry0 and the valid x range.
     static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int w, int h, int inx,
                                                    int iny, int lane, int& rx0, int& ry0, int& vspan)
@@ -192,7 +201,7 @@ struct Tracker {
             rx0 = x0;
             vspan = min(x0 + G::J_W, w) - x0 - (WW + 1);  // window origins rx0 .. rx0 + vspan are inside the region
             const int y0 = ry0;
-            stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sb, lane, [&](int row) {
+            stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sb, lane, img, [&](int row) {
                 return img + (long long)reflect_once(y0 + row, h) * pitch + x0;
             });
         } else {
@@ -210,7 +219,6 @@ struct Tracker {
                     if (lane + 32 * c < G::J_W) sb[row * (G::J_PW * 4) + lane + 32 * c] = __ldg(src + gx[c]);
             }
         }
-        __syncwarp();
     }
 
     // Template window of the previous image: WH+1 rows from ipy, bytes from x0 (returned) .. x0 + I_W
@@ -221,7 +229,7 @@ struct Tracker {
         int x0;
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~15, pitch - G::I_W);
-            stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sb, lane, [&](int row) {
+            stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sb, lane, img, [&](int row) {
                 return img + (long long)reflect_once(ipy + row, h) * pitch + x0;
             });
         } else {
@@ -247,7 +255,7 @@ struct Tracker {
         int x0;
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~3, dpitch - G::D_CH * 4);
-            stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(reinterpret_cast<uint8_t*>(sD), lane, [&](int row) -> const uint8_t* {
+            stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(reinterpret_cast<uint8_t*>(sD), lane, der, [&](int row) -> const uint8_t* {
                 const int gy = ipy + row;
                 if ((unsigned)gy >= (unsigned)h) return nullptr;
                 return reinterpret_cast<const uint8_t*>(der + (long long)gy * dpitch + x0);
@@ -307,14 +315,45 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     const bool want_err = P.err != nullptr;
     const bool get_min_eig = (P.flags & DR3LK_GET_MIN_EIGENVALS) != 0;
 
-    for (;;) {
+    // window origin of the template at `level` for previous-frame point pp; false when it is out of frame
+    auto template_origin = [&](const float2 pp, int level, int& ipx, int& ipy, float& fx, float& fy) -> bool {
+        const float sc = __int_as_float((127 - level) << 23);
+        fx = __fsub_rn(__fmul_rn(pp.x, sc), hwx);
+        fy = __fsub_rn(__fmul_rn(pp.y, sc), hwy);
+        ipx = __float2int_rd(fx); ipy = __float2int_rd(fy);
+        const LevelDesc& L = P.lv[level];
+        return (unsigned)(ipx + WW) < (unsigned)(L.w + WW) && (unsigned)(ipy + WH) < (unsigned)(L.h + WH);
+    };
+    // issue the copies of the template window (image + derivatives) of (pair, pp, level) into sI / sD
+    auto issue_template = [&](int pair, const float2 pp, int level) {
+        int ipx, ipy;
+        float fx, fy;
+        if (!template_origin(pp, level, ipx, ipy, fx, fy)) return;
+        const LevelDesc& L = P.lv[level];
+        T::stage_I(sI, L.prev + (long long)pair * L.prev_stride, L.pitch_p, L.w, L.h, ipx, ipy, lane);
+        T::stage_D(sD, L.deriv + (long long)pair * L.deriv_stride, L.dpitch, L.w, L.h, ipx, ipy, lane);
+    };
+    auto fetch = [&]() -> int {
         int f = 0;
         if (lane == 0) f = atomicAdd(P.work_counter, 1);
-        f = __shfl_sync(0xffffffffu, f, 0);
-        if (f >= P.n_total) break;
+        return __shfl_sync(0xffffffffu, f, 0);
+    };
+    auto pair_of = [&](int f) -> int { return P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f); };
 
-        const int pair = P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f);
-        const float2 pp = P.prev_pts[f];
+    int f = fetch();
+    if (f >= P.n_total) return;
+    float2 pp = P.prev_pts[f];
+    int pair = pair_of(f);
+    issue_template(pair, pp, P.max_level);
+    cp_async_commit();
+
+    for (;;) {
+        // look ahead: the next feature's coarsest template window is prefetched while this one finishes
+        const int f_next = fetch();
+        float2 pp_next = make_float2(0.f, 0.f);
+        int pair_next = 0;
+        if (f_next < P.n_total) { pp_next = P.prev_pts[f_next]; pair_next = pair_of(f_next); }
+
         float2 np = make_float2(0.f, 0.f);
         if (P.flags & DR3LK_USE_INITIAL_FLOW) np = P.next_pts[f];
 
@@ -326,61 +365,80 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             const LevelDesc& L = P.lv[level];
             const int w = L.w, h = L.h;
             const float sc = __int_as_float((127 - level) << 23);
+            const uint8_t* imgJ = L.next + (long long)pair * L.next_stride;
 
-            float px = __fmul_rn(pp.x, sc), py = __fmul_rn(pp.y, sc);
+            int ipx, ipy;
+            float px, py;
+            const bool inb = template_origin(pp, level, ipx, ipy, px, py);
             float nx, ny;
             if (level == P.max_level) {
                 if (P.flags & DR3LK_USE_INITIAL_FLOW) { nx = __fmul_rn(np.x, sc); ny = __fmul_rn(np.y, sc); }
-                else { nx = px; ny = py; }
+                else { nx = __fmul_rn(pp.x, sc); ny = __fmul_rn(pp.y, sc); }
             } else {
                 nx = __fmul_rn(np.x, 2.f); ny = __fmul_rn(np.y, 2.f);
             }
             np.x = nx; np.y = ny;
+            nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
 
-            px = __fsub_rn(px, hwx); py = __fsub_rn(py, hwy);
-            const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
-            if ((unsigned)(ipx + WW) >= (unsigned)(w + WW) || (unsigned)(ipy + WH) >= (unsigned)(h + WH)) {
-                if (level == 0) { status = 0; err = 0.f; }
-                continue;
+            // search region around the initial estimate: issued now, consumed after the template phase
+            int rx0 = 0, ry0 = 0, vspan = 0;
+            bool staged = false;
+            if (inb) {
+                const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
+                if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) {
+                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, jx, jy, lane, rx0, ry0, vspan);
+                    staged = true;
+                }
             }
-            Weights q = make_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
-
-            // ---- template: stage I and derivative windows, build (I, Ix, Iy) in registers, Gram matrix ----
-            n_templates++;
-            const uint8_t* imgI = L.prev + (long long)pair * L.prev_stride;
-            const int* der = L.deriv + (long long)pair * L.deriv_stride;
+            cp_async_commit();
+            cp_async_wait<1>();  // everything older than the search region: this level's template window has landed
             __syncwarp();
-            const int ix0 = T::stage_I(sI, imgI, L.pitch_p, w, h, ipx, ipy, lane);
-            const int dx0 = T::stage_D(sD, der, L.dpitch, w, h, ipx, ipy, lane);
-            __syncwarp();
-            const int ox = ipx - ix0, oxw = ipx - dx0;
 
             int dxr[NRUN][R], dyr[NRUN][R];
             unsigned i5p[NRUN][(R + 1) / 2];
             int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
+            Weights q;
+            if (inb) {
+                // ---- template: (I, Ix, Iy) of the window into registers, Gram matrix ----
+                n_templates++;
+                q = make_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
+                const int ox = ipx - min(ipx & ~15, L.pitch_p - G::I_W), oxw = ipx - min(ipx & ~3, L.dpitch - G::D_CH * 4);
+                const bool xin = ipx >= 0 && ipx + WW < w;  // else the byte-wise path staged from x0 = ipx
 #pragma unroll
-            for (int s = 0; s < NRUN; s++) {
-                RunBytes<R, G::NWD, G::NEO, G::I_PW> rb;
-                rb.load(sI, iofs[s] + ox);
-                const unsigned* dp = sD + dofs[s] + (rvalid[s] ? oxw : 0);
-                int tx[R + 1], ty[R + 1], bx[R + 1], by[R + 1];
+                for (int s = 0; s < NRUN; s++) {
+                    RunBytes<R, G::NWD, G::NEO, G::I_PW> rb;
+                    rb.load(sI, iofs[s] + (xin ? ox : 0));
+                    const unsigned* dp = sD + dofs[s] + ((rvalid[s] && xin) ? oxw : 0);
+                    int tx[R + 1], ty[R + 1], bx[R + 1], by[R + 1];
 #pragma unroll
-                for (int k = 0; k <= R; k++) {
-                    const int dt = (int)dp[k], db = (int)dp[G::D_PW + k];
-                    tx[k] = (short)dt; ty[k] = dt >> 16;
-                    bx[k] = (short)db; by[k] = db >> 16;
+                    for (int k = 0; k <= R; k++) {
+                        const int dt = (int)dp[k], db = (int)dp[G::D_PW + k];
+                        tx[k] = (short)dt; ty[k] = dt >> 16;
+                        bx[k] = (short)db; by[k] = db >> 16;
+                    }
+#pragma unroll
+                    for (int k = 0; k < R; k++) {
+                        const int i5 = rb.sample(k, q);
+                        int ix = (tx[k] * q.w00 + tx[k + 1] * q.w01 + bx[k] * q.w10 + bx[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                        int iy = (ty[k] * q.w00 + ty[k + 1] * q.w01 + by[k] * q.w10 + by[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                        if (G::RAGGED && k >= WW - (G::NCB - 1) * R && rlast[s]) { ix = 0; iy = 0; }  // pixels past the window edge
+                        dxr[s][k] = ix; dyr[s][k] = iy;
+                        if (k & 1) i5p[s][k >> 1] |= (unsigned)i5 << 16; else i5p[s][k >> 1] = (unsigned)i5;
+                        a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                        c1 += i5 * ix; c2 += i5 * iy;
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < R; k++) {
-                    const int i5 = rb.sample(k, q);
-                    int ix = (tx[k] * q.w00 + tx[k + 1] * q.w01 + bx[k] * q.w10 + bx[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    int iy = (ty[k] * q.w00 + ty[k + 1] * q.w01 + by[k] * q.w10 + by[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    if (G::RAGGED && k >= WW - (G::NCB - 1) * R && rlast[s]) { ix = 0; iy = 0; }  // pixels past the window edge
-                    dxr[s][k] = ix; dyr[s][k] = iy;
-                    if (k & 1) i5p[s][k >> 1] |= (unsigned)i5 << 16; else i5p[s][k >> 1] = (unsigned)i5;
-                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                    c1 += i5 * ix; c2 += i5 * iy;
-                }
+            }
+            // the template regions are free again: prefetch the next template window (next finer level of this
+            // feature, or the coarsest level of the next feature) behind the iterations
+            __syncwarp();
+            if (level > 0) issue_template(pair, pp, level - 1);
+            else if (f_next < P.n_total) issue_template(pair_next, pp_next, P.max_level);
+            cp_async_commit();
+
+            if (!inb) {
+                if (level == 0) { status = 0; err = 0.f; }
+                continue;
             }
             const HiLo s11 = warp_sum_hilo(a11), s12 = warp_sum_hilo(a12), s22 = warp_sum_hilo(a22);
             const HiLo sc1 = warp_sum_hilo(c1), sc2 = warp_sum_hilo(c2);
@@ -403,11 +461,10 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             D = __fdiv_rn(1.f, D);
 
             // ---- iterations ----
-            const uint8_t* imgJ = L.next + (long long)pair * L.next_stride;
-            nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+            cp_async_wait<1>();  // the search region has landed (the template prefetch may still be in flight)
+            __syncwarp();
             float pdx = 0.f, pdy = 0.f;
-            int rx0 = 0, ry0 = 0, vspan = 0;
-            bool staged = false, moved = false;
+            bool moved = false;
             for (int j = 0; j < P.max_count; ++j) {
                 const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
                 if ((unsigned)(inx + WW) >= (unsigned)(w + WW) || (unsigned)(iny + WH) >= (unsigned)(h + WH)) {
@@ -416,7 +473,11 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 }
                 q = make_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
                 if (!staged || (unsigned)(inx - rx0) > (unsigned)vspan || (unsigned)(iny - ry0) > (unsigned)(2 * G::MY)) {
+                    __syncwarp();
                     T::stage_J(sJ, imgJ, L.pitch_n, w, h, inx, iny, lane, rx0, ry0, vspan);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    __syncwarp();
                     staged = true;
                 }
                 const int jbase = (iny - ry0) * (G::J_PW * 4) + (inx - rx0);
@@ -466,8 +527,13 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     continue;
                 }
                 q = make_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy));
-                if (!staged || (unsigned)(iqx - rx0) > (unsigned)vspan || (unsigned)(iqy - ry0) > (unsigned)(2 * G::MY))
+                if (!staged || (unsigned)(iqx - rx0) > (unsigned)vspan || (unsigned)(iqy - ry0) > (unsigned)(2 * G::MY)) {
+                    __syncwarp();
                     T::stage_J(sJ, imgJ, L.pitch_n, w, h, iqx, iqy, lane, rx0, ry0, vspan);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    __syncwarp();
+                }
                 const int jbase = (iqy - ry0) * (G::J_PW * 4) + (iqx - rx0);
                 int es = 0;
 #pragma unroll
@@ -495,7 +561,10 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             if (want_err) P.err[f] = err;
             if (P.stats) P.stats[f] = (n_iters & 0xffffu) | ((n_templates & 0xffu) << 16) | (err_pass << 24);
         }
+        if (f_next >= P.n_total) break;
+        f = f_next; pp = pp_next; pair = pair_next;
     }
+    cp_async_wait<0>();
 }
 
 template <typename G>
