@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdr3lk.so")
+LIB_PATH = os.environ.get("DR3LK_LIB", os.path.join(_HERE, "lib", "libdr3lk.so"))  # override only for A/B kernel experiments
 
 OK, E_ARG, E_SIZE, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4
 TERM_COUNT, TERM_EPS = 1, 2

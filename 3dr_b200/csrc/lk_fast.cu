@@ -100,13 +100,16 @@ struct Weights {
 __device__ __forceinline__ Weights make_weights(float a, float b)
 {
     Weights q;
-    const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
-    q.w00 = __float2int_rn(__fmul_rn(__fmul_rn(oma, omb), 16384.f));
-    q.w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, omb), 16384.f));
-    q.w10 = __float2int_rn(__fmul_rn(__fmul_rn(oma, b), 16384.f));
+    // rn(x * y) * 2^14 == rn(x * (y * 2^14)): scaling by a power of two is exact (no under/overflow here), so the
+    // scale is folded into one factor; the products round exactly as OpenCV's (1-a)*(1-b)*(1<<14) does.
+    const float oma = __fsub_rn(1.f, a);
+    const float ombs = __fmul_rn(__fsub_rn(1.f, b), 16384.f), bs = __fmul_rn(b, 16384.f);
+    q.w00 = __float2int_rn(__fmul_rn(oma, ombs));
+    q.w01 = __float2int_rn(__fmul_rn(a, ombs));
+    q.w10 = __float2int_rn(__fmul_rn(oma, bs));
     q.w11 = (1 << W_BITS) - q.w00 - q.w01 - q.w10;
-    q.wt = (q.w00 & 0xffff) | (q.w01 << 16);
-    q.wb = (q.w10 & 0xffff) | (q.w11 << 16);
+    q.wt = (int)__byte_perm((unsigned)q.w00, (unsigned)q.w01, 0x5410);  // low halves: w00 | w01 << 16
+    q.wb = (int)__byte_perm((unsigned)q.w10, (unsigned)q.w11, 0x5410);
     return q;
 }
 
@@ -202,8 +205,8 @@ struct Tracker {
             vspan = min(x0 + G::J_W, w) - x0 - (WW + 1);  // window origins rx0 .. rx0 + vspan are inside the region
             const int y0 = ry0;
             stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sb, lane, img, [&](int row) {
-                return img + (long long)reflect_once(y0 + row, h) * pitch + x0;
-            });
+                    return img + (long long)reflect_once(y0 + row, h) * pitch + x0;
+                });
         } else {
             // window touches the left/right border: byte-wise with reflection in x and y
             rx0 = inx - (G::J_W - (WW + 1)) / 2;
@@ -230,8 +233,8 @@ struct Tracker {
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~15, pitch - G::I_W);
             stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sb, lane, img, [&](int row) {
-                return img + (long long)reflect_once(ipy + row, h) * pitch + x0;
-            });
+                    return img + (long long)reflect_once(ipy + row, h) * pitch + x0;
+                });
         } else {
             x0 = ipx;
             int gx[(G::I_W + 31) / 32];
@@ -256,10 +259,10 @@ struct Tracker {
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~3, dpitch - G::D_CH * 4);
             stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(reinterpret_cast<uint8_t*>(sD), lane, der, [&](int row) -> const uint8_t* {
-                const int gy = ipy + row;
-                if ((unsigned)gy >= (unsigned)h) return nullptr;
-                return reinterpret_cast<const uint8_t*>(der + (long long)gy * dpitch + x0);
-            });
+                    const int gy = ipy + row;
+                    if ((unsigned)gy >= (unsigned)h) return nullptr;
+                    return reinterpret_cast<const uint8_t*>(der + (long long)gy * dpitch + x0);
+                });
         } else {
             x0 = ipx;
 #pragma unroll 2
