@@ -622,8 +622,6 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         chunk_pairs = std::min(chunk_pairs, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
     }
     chunk_pairs = std::min(chunk_pairs, batch);
-    const int pitch0 = align_up(w, 16);
-    const size_t img_bytes = (size_t)pitch0 * h;
     const int n_chunks = (batch + chunk_pairs - 1) / chunk_pairs;
     std::vector<int> offs_host;  // all chunks' rebased offsets; must outlive the async copies
     offs_host.reserve((size_t)batch + n_chunks);
@@ -640,30 +638,22 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         const int b0 = c * chunk_pairs, b1 = std::min(batch, b0 + chunk_pairs), nb = b1 - b0;
         const int p0 = pts_offset[b0], n = pts_offset[b1] - p0;
         if (n == 0) continue;
-        CU_TRY(ctx, W.lvl0_prev.reserve(img_bytes * nb));
-        CU_TRY(ctx, W.lvl0_next.reserve(img_bytes * nb));
+        // Level-0 pixels cross PCIe as ONE contiguous copy per frame set in the caller's own layout (2-D copies with an
+        // odd row step are DMA-unfriendly); track_batch_device re-pitches on the device when the layout is not 16-B aligned.
+        const size_t span = image_stride * (size_t)(nb - 1) + step * (size_t)(h - 1) + w;
+        CU_TRY(ctx, W.lvl0_prev.reserve(span + 16));
+        CU_TRY(ctx, W.lvl0_next.reserve(span + 16));
         const size_t o_prev = 0, o_next = 8 * (size_t)n, o_err = 16 * (size_t)n, o_stats = 20 * (size_t)n, o_status = 24 * (size_t)n;
         CU_TRY(ctx, W.pts.reserve(25 * (size_t)n + 16));
         CU_TRY(ctx, W.offs.reserve(sizeof(int) * (size_t)(nb + 1)));
         uint8_t* dp = (uint8_t*)W.pts.p;
-        if (step == (size_t)pitch0 && image_stride == img_bytes) {
-            CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_prev.p, prev + (size_t)b0 * image_stride, img_bytes * nb, cudaMemcpyHostToDevice, st));
-            CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_next.p, next + (size_t)b0 * image_stride, img_bytes * nb, cudaMemcpyHostToDevice, st));
-        } else if (image_stride == step * (size_t)h) {
-            // images back to back: one 2-D copy re-pitches all rows of the chunk
-            CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_prev.p, pitch0, prev + (size_t)b0 * image_stride, step, w, (size_t)h * nb, cudaMemcpyHostToDevice, st));
-            CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_next.p, pitch0, next + (size_t)b0 * image_stride, step, w, (size_t)h * nb, cudaMemcpyHostToDevice, st));
-        } else {
-            for (int b = 0; b < nb; b++) {
-                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.lvl0_prev.p + img_bytes * b, pitch0, prev + (size_t)(b0 + b) * image_stride, step, w, h, cudaMemcpyHostToDevice, st));
-                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.lvl0_next.p + img_bytes * b, pitch0, next + (size_t)(b0 + b) * image_stride, step, w, h, cudaMemcpyHostToDevice, st));
-            }
-        }
+        CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_prev.p, prev + (size_t)b0 * image_stride, span, cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(W.lvl0_next.p, next + (size_t)b0 * image_stride, span, cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaMemcpyAsync(dp + o_prev, prev_pts + 2 * (size_t)p0, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
         if (flags & DR3LK_USE_INITIAL_FLOW)
             CU_TRY(ctx, cudaMemcpyAsync(dp + o_next, next_pts + 2 * (size_t)p0, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs_host.data() + offs_pos[c], sizeof(int) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
-        rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, nb,
+        rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, step, image_stride, nb,
                                 (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
                                 offs_host.data() + offs_pos[c], (const int*)W.offs.p, n, stats ? (uint32_t*)(dp + o_stats) : nullptr, a);
         if (rc != DR3LK_OK) return rc;

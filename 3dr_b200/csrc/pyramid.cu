@@ -1,7 +1,7 @@
 // Pyramid kernels of the dr3lk path (sm_100a).
 //
-//  * pyr_level_kernel  -- one launch per pyramid level for a batch of images: stages a (2*TOX+4) x (2*TOY+4)
-//    uint8 source tile (halo 2, REFLECT_101 by index reflection) in shared memory once and produces from it
+//  * pyr_level_kernel  -- one launch per pyramid level for a batch of images: stages a 160 x 36 uint8 source tile
+//    (16-byte vectorised row loads, halo, REFLECT_101 by index reflection) in shared memory once and produces from it
 //      - the next Gaussian level: OpenCV pyrDown, separable [1 4 6 4 1], (sum+128)>>8   (SURVEY.md A.2), and
 //      - the Scharr derivative of the source level as packed int16x2 (Ix, Iy)            (SURVEY.md A.3),
 //    i.e. the derivative is fused into the pyramid build: the level is read from HBM exactly once.
@@ -15,80 +15,127 @@ namespace {
 
 constexpr int TOX = 64;            // output (down-sampled) tile
 constexpr int TOY = 16;
-constexpr int SW = 2 * TOX + 4;    // source tile incl. halo 2
-constexpr int SH = 2 * TOY + 4;
-constexpr int SPITCH = SW + 4;     // 136
+constexpr int HX = 16;             // x halo of the source tile: 16 keeps every tile row 16-byte aligned (2 are needed)
+constexpr int SW = 2 * TOX + 2 * HX;   // 160 source bytes per tile row = 10 chunks of 16
+constexpr int SH = 2 * TOY + 4;        // 36 source rows (halo 2)
+constexpr int SPITCH = SW + 16;        // 176
 constexpr int PYR_THREADS = 256;
 
+__device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+// One pyramid level for a batch of images.  The source tile is staged once with 16-byte row-coalesced loads (interior
+// tiles of 16-B aligned images) or byte-wise with REFLECT_101 index reflection (edge tiles / unaligned sources); the
+// next Gaussian level (pyrDown) and the Scharr derivative of the source level are both produced from that tile.
 template <bool DOWN, bool DERIV>
 __global__ void __launch_bounds__(PYR_THREADS)
-pyr_level_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, long long src_stride,
+pyr_level_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, long long src_stride, int src_aligned,
                  uint8_t* __restrict__ dst, int dst_pitch, long long dst_stride, int* __restrict__ deriv, int dpitch,
                  long long deriv_stride)
 {
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
-    __shared__ short hrow[DOWN ? SH : 1][DOWN ? TOX : 1];
+    __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
 
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
-    const int x0 = blockIdx.x * (2 * TOX) - 2;  // source coordinate of tile[0][0]
-    const int y0 = blockIdx.y * (2 * TOY) - 2;
+    const int xs = blockIdx.x * (2 * TOX);      // first source column this tile produces derivatives for
+    const int ys = blockIdx.y * (2 * TOY);
+    const int x0 = xs - HX;                     // source coordinate of tile[0][0]
+    const int y0 = ys - 2;
     const uint8_t* s = src + (long long)img * src_stride;
 
-    const bool interior = x0 >= 0 && y0 >= 0 && x0 + SW <= w && y0 + SH <= h;
-    if (interior) {
-        for (int idx = tid; idx < SH * SW; idx += PYR_THREADS) {
-            int ty = idx / SW, tx = idx - ty * SW;
-            tile[ty][tx] = __ldg(s + (long long)(y0 + ty) * src_pitch + x0 + tx);
+    // columns xs-2 .. xs+2*TOX+1 are needed; the vector path also requires the 16-byte chunks to stay inside the row
+    const bool xin = src_aligned && blockIdx.x >= 1 && xs + 2 * TOX + 2 <= w && x0 + SW <= src_pitch;
+    if (xin) {
+        for (int idx = tid; idx < SH * (SW / 16); idx += PYR_THREADS) {
+            const int ty = idx / (SW / 16), ch = idx - ty * (SW / 16);
+            const int sy = reflect101(y0 + ty, h);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(s + (long long)sy * src_pitch + x0 + ch * 16));
+            *reinterpret_cast<uint4*>(&tile[ty][ch * 16]) = v;
         }
     } else {
-        for (int idx = tid; idx < SH * SW; idx += PYR_THREADS) {
-            int ty = idx / SW, tx = idx - ty * SW;
-            int sx = reflect101(x0 + tx, w), sy = reflect101(y0 + ty, h);
+        for (int idx = tid; idx < SH * (2 * TOX + 4); idx += PYR_THREADS) {
+            const int ty = idx / (2 * TOX + 4), tx = HX - 2 + (idx - ty * (2 * TOX + 4));
+            const int sx = reflect101(x0 + tx, w), sy = reflect101(y0 + ty, h);
             tile[ty][tx] = __ldg(s + (long long)sy * src_pitch + sx);
         }
     }
     __syncthreads();
 
     if (DERIV) {
-        // source pixel (sx, sy) sits at tile[sy - y0][sx - x0] = tile[ly + 2][lx + 2]
-        const int lx = tid & (2 * TOX - 1);
+        // 4 consecutive pixels per thread: source (xs + 4g .. +3, ys + ly) <-> tile[ly + 2][HX + 4g ..]
+        const int g = tid & 31;
         int* d = deriv + (long long)img * deriv_stride;
-        for (int ly = tid / (2 * TOX); ly < 2 * TOY; ly += PYR_THREADS / (2 * TOX)) {
-            const int sx = x0 + 2 + lx, sy = y0 + 2 + ly;
+        for (int ly = tid >> 5; ly < 2 * TOY; ly += PYR_THREADS / 32) {
+            const int sx = xs + 4 * g, sy = ys + ly;
             if (sx < w && sy < h) {
-                const uint8_t* r0 = &tile[ly + 1][lx + 1];
-                const uint8_t* r1 = &tile[ly + 2][lx + 1];
-                const uint8_t* r2 = &tile[ly + 3][lx + 1];
-                int a0 = r0[0], a1 = r0[1], a2 = r0[2];
-                int b0 = r1[0], b2 = r1[2];
-                int c0 = r2[0], c1 = r2[1], c2 = r2[2];
-                // t0 = 3*(up+down) + 10*mid (vertical smooth), t1 = down - up (vertical difference)
-                int t0l = 3 * (a0 + c0) + 10 * b0, t0r = 3 * (a2 + c2) + 10 * b2;
-                int t1l = c0 - a0, t1m = c1 - a1, t1r = c2 - a2;
-                int ix = t0r - t0l;
-                int iy = 3 * (t1l + t1r) + 10 * t1m;
-                d[(long long)sy * dpitch + sx] = (ix & 0xffff) | (iy << 16);
+                int t0[6], t1[6];
+                const unsigned* r0 = reinterpret_cast<const unsigned*>(&tile[ly + 1][HX - 4 + 4 * g]);
+                const unsigned* r1 = reinterpret_cast<const unsigned*>(&tile[ly + 2][HX - 4 + 4 * g]);
+                const unsigned* r2 = reinterpret_cast<const unsigned*>(&tile[ly + 3][HX - 4 + 4 * g]);
+                const unsigned a0 = r0[0], a1 = r0[1], a2 = r0[2];
+                const unsigned b0 = r1[0], b1 = r1[1], b2 = r1[2];
+                const unsigned c0 = r2[0], c1 = r2[1], c2 = r2[2];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {   // column sx - 1 + i = byte 3 + i of the 12 loaded bytes
+                    const int k = 3 + i;
+                    const int a = (int)byte_of(k < 4 ? a0 : (k < 8 ? a1 : a2), k & 3);
+                    const int b = (int)byte_of(k < 4 ? b0 : (k < 8 ? b1 : b2), k & 3);
+                    const int c = (int)byte_of(k < 4 ? c0 : (k < 8 ? c1 : c2), k & 3);
+                    t0[i] = 3 * (a + c) + 10 * b;   // vertical smooth
+                    t1[i] = c - a;                  // vertical difference
+                }
+                int o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int ix = t0[j + 2] - t0[j];
+                    const int iy = 3 * (t1[j] + t1[j + 2]) + 10 * t1[j + 1];
+                    o[j] = (ix & 0xffff) | (iy << 16);
+                }
+                int* out = d + (long long)sy * dpitch + sx;
+                if (sx + 3 < w) {
+                    *reinterpret_cast<int4*>(out) = make_int4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (sx + j < w) out[j] = o[j];
+                }
             }
         }
     }
 
     if (DOWN) {
-        for (int idx = tid; idx < SH * TOX; idx += PYR_THREADS) {
-            int ty = idx / TOX, ox = idx - ty * TOX;
-            const uint8_t* r = &tile[ty][2 * ox];
-            hrow[ty][ox] = (short)(r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
+        // horizontal [1 4 6 4 1]: 2 outputs per thread, output ox reads tile columns HX - 2 + 2*ox .. + 4
+        const int m = tid & 31;
+        for (int ty = tid >> 5; ty < SH; ty += PYR_THREADS / 32) {
+            const unsigned* r = reinterpret_cast<const unsigned*>(&tile[ty][HX - 4 + 4 * m]);
+            const unsigned w0 = r[0], w1 = r[1], w2 = r[2];
+            const int b2 = byte_of(w0, 2), b3 = byte_of(w0, 3), b4 = byte_of(w1, 0), b5 = byte_of(w1, 1), b6 = byte_of(w1, 2),
+                      b7 = byte_of(w1, 3), b8 = byte_of(w2, 0);
+            const int h0 = b2 + 4 * b3 + 6 * b4 + 4 * b5 + b6;
+            const int h1 = b4 + 4 * b5 + 6 * b6 + 4 * b7 + b8;
+            *reinterpret_cast<short2*>(&hrow[ty][2 * m]) = make_short2((short)h0, (short)h1);
         }
         __syncthreads();
         const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
         uint8_t* o = dst + (long long)img * dst_stride;
-        const int ox = tid & (TOX - 1);
-        for (int oy = tid / TOX; oy < TOY; oy += PYR_THREADS / TOX) {
-            const int gx = blockIdx.x * TOX + ox, gy = blockIdx.y * TOY + oy;
-            if (gx < dw && gy < dh) {
-                int v = hrow[2 * oy][ox] + 4 * hrow[2 * oy + 1][ox] + 6 * hrow[2 * oy + 2][ox] + 4 * hrow[2 * oy + 3][ox] +
-                        hrow[2 * oy + 4][ox];
-                o[(long long)gy * dst_pitch + gx] = (uint8_t)((v + 128) >> 8);
+        const int q = tid & 15, oy = tid >> 4;   // 4 outputs per thread, 16 threads per row, 16 rows
+        const int gx = blockIdx.x * TOX + 4 * q, gy = blockIdx.y * TOY + oy;
+        if (gx < dw && gy < dh) {
+            int v[4] = {128, 128, 128, 128};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const short4 hv = *reinterpret_cast<const short4*>(&hrow[2 * oy + k][4 * q]);
+                const int c = (k == 0 || k == 4) ? 1 : (k == 2 ? 6 : 4);
+                v[0] += c * hv.x; v[1] += c * hv.y; v[2] += c * hv.z; v[3] += c * hv.w;
+            }
+            uint8_t* out = o + (long long)gy * dst_pitch + gx;
+            if (gx + 3 < dw && (dst_pitch & 3) == 0) {
+                *reinterpret_cast<unsigned*>(out) = (unsigned)(v[0] >> 8) | ((unsigned)(v[1] >> 8) << 8) | ((unsigned)(v[2] >> 8) << 16) |
+                                                    ((unsigned)(v[3] >> 8) << 24);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (gx + j < dw) out[j] = (uint8_t)(v[j] >> 8);
             }
         }
     }
@@ -123,14 +170,15 @@ void launch_pyr_level(Launch& L, const uint8_t* src, int w, int h, int src_pitch
 {
     if (L.err != cudaSuccess || n_img <= 0) return;
     dim3 grid((w + 2 * TOX - 1) / (2 * TOX), (h + 2 * TOY - 1) / (2 * TOY), n_img);
+    const int aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_stride) & 15) == 0;
     if (dst && deriv)
-        pyr_level_kernel<true, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, dst, dst_pitch,
+        pyr_level_kernel<true, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, dst, dst_pitch,
                                                                        dst_stride, deriv, dpitch, deriv_stride);
     else if (dst)
-        pyr_level_kernel<true, false><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, dst, dst_pitch,
+        pyr_level_kernel<true, false><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, dst, dst_pitch,
                                                                         dst_stride, nullptr, 0, 0);
     else if (deriv)
-        pyr_level_kernel<false, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, nullptr, 0, 0,
+        pyr_level_kernel<false, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, nullptr, 0, 0,
                                                                         deriv, dpitch, deriv_stride);
     else
         return;

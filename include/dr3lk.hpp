@@ -1,0 +1,148 @@
+// dr3lk.hpp -- C++14 host shim over the C ABI (dr3lk.h) that keeps the reference's call surface for this path.
+//
+//   dr3::calcOpticalFlowPyrLK(...)   same arguments, defaults, output sizing and error behaviour as
+//                                    cv::calcOpticalFlowPyrLK, which the reference calls at src/initialization.cpp:608-613
+//   dr3::create_img_pyramid(...)     utils::create_img_pyramid of the reference (include/utils.hpp:67, src/utils.cpp:421-430)
+//
+// No OpenCV headers are needed: images are passed as dr3::Image views (data / cols / rows / step -- exactly the
+// cv::Mat fields, see dr3::view()), points as any 2-float struct (cv::Point2f works unchanged).
+// Header-only; link with libdr3lk.so.  There is no CPU fallback: without a CUDA device the first call throws.
+#ifndef DR3LK_HPP_
+#define DR3LK_HPP_
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dr3lk.h"
+
+namespace dr3 {
+
+struct Size {
+    int width, height;
+    Size(int w = 0, int h = 0) : width(w), height(h) {}
+};
+struct Point2f {
+    float x, y;
+    Point2f(float x_ = 0.f, float y_ = 0.f) : x(x_), y(y_) {}
+};
+struct TermCriteria {
+    enum Type { COUNT = 1, MAX_ITER = COUNT, EPS = 2 };
+    int type, maxCount;
+    double epsilon;
+    TermCriteria(int t = COUNT + EPS, int c = 30, double e = 0.01) : type(t), maxCount(c), epsilon(e) {}
+};
+enum { OPTFLOW_USE_INITIAL_FLOW = DR3LK_USE_INITIAL_FLOW, OPTFLOW_LK_GET_MIN_EIGENVALS = DR3LK_GET_MIN_EIGENVALS };
+
+// Thrown where OpenCV would throw cv::Exception (CV_Assert failures) and on CUDA errors.
+class Exception : public std::runtime_error {
+public:
+    int code;
+    Exception(int c, const std::string& m) : std::runtime_error("dr3lk error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+// Non-owning view of a CV_8UC1 image.
+struct Image {
+    const uint8_t* data;
+    int cols, rows;
+    size_t step;
+    Image() : data(nullptr), cols(0), rows(0), step(0) {}
+    Image(const uint8_t* d, int c, int r, size_t s) : data(d), cols(c), rows(r), step(s) {}
+    bool empty() const { return data == nullptr || cols <= 0 || rows <= 0; }
+};
+// view(cv::Mat) -- anything with data / cols / rows / step (size_t-convertible) members.
+template <class Mat>
+inline Image view(const Mat& m) { return Image(reinterpret_cast<const uint8_t*>(m.data), m.cols, m.rows, static_cast<size_t>(m.step)); }
+
+// Owning continuous CV_8UC1 image (the levels create_img_pyramid allocates, like `cv::Mat(rows, cols, CV_8U)`).
+struct OwnedImage {
+    std::shared_ptr<std::vector<uint8_t>> buf;  // null for level 0: that level aliases the caller's buffer (shallow copy)
+    const uint8_t* data;
+    int cols, rows;
+    size_t step;
+    OwnedImage() : data(nullptr), cols(0), rows(0), step(0) {}
+    operator Image() const { return Image(data, cols, rows, step); }
+};
+typedef std::vector<OwnedImage> ImgPyramid;  // reference: typedef std::vector<cv::Mat> ImgPyramid (include/global.hpp:33)
+
+// One dr3lk_ctx per host thread (the reference calls the path from a single thread, src/handler.cpp:31-48).
+class Context {
+public:
+    explicit Context(int device = 0) : ctx_(nullptr)
+    {
+        const int rc = dr3lk_create(&ctx_, device);
+        if (rc != DR3LK_OK) throw Exception(rc, dr3lk_last_error(nullptr));
+    }
+    ~Context() { dr3lk_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    dr3lk_ctx* get() const { return ctx_; }
+    void check(int rc) const
+    {
+        if (rc != DR3LK_OK) throw Exception(rc, dr3lk_last_error(ctx_));
+    }
+    static Context& thread_default()
+    {
+        static thread_local Context c(0);
+        return c;
+    }
+
+private:
+    dr3lk_ctx* ctx_;
+};
+
+// cv::calcOpticalFlowPyrLK.  P2f: any struct of two floats (x, y), e.g. cv::Point2f or dr3::Point2f.
+template <class P2f>
+inline void calcOpticalFlowPyrLK(const Image& prevImg, const Image& nextImg, const std::vector<P2f>& prevPts, std::vector<P2f>& nextPts,
+                                 std::vector<unsigned char>& status, std::vector<float>& err, Size winSize = Size(21, 21), int maxLevel = 3,
+                                 TermCriteria criteria = TermCriteria(TermCriteria::COUNT + TermCriteria::EPS, 30, 0.01), int flags = 0,
+                                 double minEigThreshold = 1e-4, Context* context = nullptr)
+{
+    static_assert(sizeof(P2f) == 2 * sizeof(float), "points must be two packed floats (x, y)");
+    Context& c = context ? *context : Context::thread_default();
+    if (maxLevel < 0 || winSize.width <= 2 || winSize.height <= 2)
+        throw Exception(DR3LK_E_ARG, "(-215:Assertion failed) maxLevel >= 0 && winSize.width > 2 && winSize.height > 2");
+    const size_t n = prevPts.size();
+    if (n == 0) {  // OpenCV: nextPts / status / err are released
+        nextPts.clear(); status.clear(); err.clear();
+        return;
+    }
+    if (prevImg.empty() || nextImg.empty() || prevImg.cols != nextImg.cols || prevImg.rows != nextImg.rows)
+        throw Exception(DR3LK_E_SIZE, "(-215:Assertion failed) prevPyr[level * lvlStep1].size() == nextPyr[level * lvlStep2].size()");
+    if (flags & OPTFLOW_USE_INITIAL_FLOW) {
+        if (nextPts.size() != n)
+            throw Exception(DR3LK_E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints");
+    } else {
+        nextPts.resize(n);
+    }
+    status.resize(n);
+    err.resize(n);
+    c.check(dr3lk_calc_optical_flow_pyr_lk(c.get(), prevImg.data, prevImg.step, nextImg.data, nextImg.step, prevImg.cols, prevImg.rows,
+                                           reinterpret_cast<const float*>(prevPts.data()), reinterpret_cast<float*>(nextPts.data()),
+                                           status.data(), err.data(), static_cast<int>(n), winSize.width, winSize.height, maxLevel,
+                                           criteria.type, criteria.maxCount, criteria.epsilon, flags, minEigThreshold));
+}
+
+// utils::create_img_pyramid(img_lvl_0, n_levels, pyr): pyr[0] aliases the input, pyr[i] is rows/2 x cols/2 of pyr[i-1].
+// `mode` selects the rounding of utils::reduce_to_half; the default reproduces the reference on x86.
+inline void create_img_pyramid(const Image& img_lvl_0, int n_levels, ImgPyramid& pyr, int mode = DR3LK_BOX_AUTO_X86, Context* context = nullptr)
+{
+    Context& c = context ? *context : Context::thread_default();
+    pyr.assign(static_cast<size_t>(n_levels > 0 ? n_levels : 0), OwnedImage());
+    if (n_levels <= 0) return;
+    pyr[0].data = img_lvl_0.data; pyr[0].cols = img_lvl_0.cols; pyr[0].rows = img_lvl_0.rows; pyr[0].step = img_lvl_0.step;
+    std::vector<uint8_t*> outs;
+    int w = img_lvl_0.cols, h = img_lvl_0.rows;
+    for (int l = 1; l < n_levels; l++) {
+        w /= 2; h /= 2;
+        pyr[l].buf = std::make_shared<std::vector<uint8_t>>(static_cast<size_t>(w > 0 ? w : 0) * static_cast<size_t>(h > 0 ? h : 0));
+        pyr[l].data = pyr[l].buf->data(); pyr[l].cols = w; pyr[l].rows = h; pyr[l].step = static_cast<size_t>(w);
+        outs.push_back(pyr[l].buf->data());
+    }
+    c.check(dr3lk_box_pyramid(c.get(), img_lvl_0.data, img_lvl_0.cols, img_lvl_0.rows, img_lvl_0.step, n_levels, outs.data(), mode));
+}
+
+}  // namespace dr3
+#endif  // DR3LK_HPP_

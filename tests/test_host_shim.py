@@ -1,0 +1,47 @@
+"""GPU test of the C++14 host shim: the compiled mirror of the reference call site (3dr_b200/host/init_frontend.cpp,
+built against include/dr3lk.hpp) must reproduce the oracle run with the reference's literal parameters."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from _common import ROOT, golden_case, load_gray
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_pgm(path, img):
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img).tobytes())
+
+
+def test_init_frontend_matches_oracle(tmp_path):
+    exe = os.path.join(ROOT, "3dr_b200", "host", "init_frontend")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = golden_case("c1_reference_30x30_initflow")["prev_pts"][:1500]
+    _write_pgm(tmp_path / "a.pgm", a)
+    _write_pgm(tmp_path / "b.pgm", b)
+    np.savetxt(tmp_path / "pts.txt", pts, fmt="%.9g")
+    r = subprocess.run([exe, str(tmp_path / "a.pgm"), str(tmp_path / "b.pgm"), str(tmp_path / "pts.txt"), str(tmp_path / "out.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Outlier count from optical flow" in r.stdout and "Average disparity" in r.stdout
+    with open(tmp_path / "out.txt") as f:
+        lines = f.read().split("\n")
+    outliers, matches, mean_disp = lines[0].split()
+    # the reference's literal call: 30x30, maxLevel 4, (COUNT+EPS, 1000, 1e-3), OPTFLOW_USE_INITIAL_FLOW with nextPts = prevPts
+    p, s, e = oracle.calc_optical_flow_pyr_lk(a, b, pts, pts.copy(), (30, 30), 4, (3, 1000, 1e-3), 4)
+    assert int(outliers) == int((s == 0).sum()) and int(matches) == int(s.sum())
+    disp = np.linalg.norm(pts[s == 1].astype(np.float64) - p[s == 1].astype(np.float64), axis=1)
+    assert abs(float(mean_disp) - disp.mean()) < 1e-5
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[3:] if ln.strip()], np.float64)
+    assert rows.shape == (int(s.sum()), 4)
+    assert np.abs(rows[:, 0:2] - pts[s == 1]).max() < 1e-4 and np.abs(rows[:, 2:4] - p[s == 1]).max() < 1e-4
+    box = oracle.box_pyramid(a, 3)
+    assert [int(v) for v in lines[1].split()] == [620, 188, 310, 94]
+    assert [int(v) for v in lines[2].split()] == [int(box[1].sum()), int(box[2].sum())]
