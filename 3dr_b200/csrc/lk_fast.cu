@@ -147,8 +147,6 @@ struct RunBytes {
     }
 };
 
-__device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -167,24 +165,29 @@ template <typename G>
 struct Tracker {
     static constexpr int WW = G::WW, WH = G::WH;
 
-    // Rows of 16-byte chunks, LPR (power of two) lanes per row: global -> shared with cp.async (LDGSTS, no registers,
-    // completion tracked per commit group).  row_ptr(row) returns the global address of the row's first chunk, or
-    // nullptr for a row of zeros (src-size 0 zero-fills).
-    template <int NROWS, int CH, int PITCH_BYTES, typename RowPtr>
-    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, const void* any_valid_global, RowPtr row_ptr)
+    // NROWS rows of CH 16-byte chunks, LPR (power of two) lanes per row: global -> shared with cp.async (LDGSTS: no
+    // registers, completion tracked per commit group).  `base` points at the first chunk of image row 0; row r of the
+    // region is image row y0 + r, reflected into the image (REFLECT_101) or, with ZERO_OUTSIDE, zero-filled when it
+    // lies outside (src-size 0; the address is still the reflected, valid row).
+    template <int NROWS, int CH, int PITCH_BYTES, bool ZERO_OUTSIDE>
+    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, const uint8_t* base, int pitch_bytes, int y0, int h)
     {
         constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = (NROWS + RPR - 1) / RPR;
         const int ch = lane & (LPR - 1), rr = lane / LPR;
+        if (ch >= CH) return;
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(sb) + rr * PITCH_BYTES + ch * 16;
+        const uint8_t* cbase = base + ch * 16;
 #pragma unroll
         for (int i = 0; i < ROUNDS; i++) {
             const int row = rr + i * RPR;
-            if (row < NROWS && ch < CH) {
-                const uint8_t* src = row_ptr(row);
-                const int nbytes = src ? 16 : 0;
-                const void* g = src ? (const void*)(src + ch * 16) : any_valid_global;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g), "r"(nbytes)
-                             : "memory");
+            if ((i + 1) * RPR > NROWS && row >= NROWS) break;
+            const int gy = y0 + row;
+            const uint8_t* g = cbase + (long long)reflect_once(gy, h) * pitch_bytes;
+            if (ZERO_OUTSIDE) {
+                const int nbytes = (unsigned)gy < (unsigned)h ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g), "r"(nbytes) : "memory");
+            } else {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g) : "memory");
             }
         }
     }
@@ -203,10 +206,7 @@ struct Tracker {
             x0 = max(0, min(x0, pitch - G::J_W));
             rx0 = x0;
             vspan = min(x0 + G::J_W, w) - x0 - (WW + 1);  // window origins rx0 .. rx0 + vspan are inside the region
-            const int y0 = ry0;
-            stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sb, lane, img, [&](int row) {
-                    return img + (long long)reflect_once(y0 + row, h) * pitch + x0;
-                });
+            stage_rows<G::J_H, G::J_CH, G::J_PW * 4, false>(sb, lane, img + x0, pitch, ry0, h);
         } else {
             // window touches the left/right border: byte-wise with reflection in x and y
             rx0 = inx - (G::J_W - (WW + 1)) / 2;
@@ -232,9 +232,7 @@ struct Tracker {
         int x0;
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~15, pitch - G::I_W);
-            stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sb, lane, img, [&](int row) {
-                    return img + (long long)reflect_once(ipy + row, h) * pitch + x0;
-                });
+            stage_rows<WH + 1, G::I_CH, G::I_PW * 4, false>(sb, lane, img + x0, pitch, ipy, h);
         } else {
             x0 = ipx;
             int gx[(G::I_W + 31) / 32];
@@ -258,11 +256,8 @@ struct Tracker {
         int x0;
         if (ipx >= 0 && ipx + WW < w) {
             x0 = min(ipx & ~3, dpitch - G::D_CH * 4);
-            stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(reinterpret_cast<uint8_t*>(sD), lane, der, [&](int row) -> const uint8_t* {
-                    const int gy = ipy + row;
-                    if ((unsigned)gy >= (unsigned)h) return nullptr;
-                    return reinterpret_cast<const uint8_t*>(der + (long long)gy * dpitch + x0);
-                });
+            stage_rows<WH + 1, G::D_CH, G::D_PW * 4, true>(reinterpret_cast<uint8_t*>(sD), lane, reinterpret_cast<const uint8_t*>(der + x0),
+                                                          dpitch * 4, ipy, h);
         } else {
             x0 = ipx;
 #pragma unroll 2

@@ -130,8 +130,26 @@ def cpu_reference(prev, nxt, pts, offs, n_pairs, threads=None):
     return {"tracked": tracked, "features": feats, "seconds": dt, "kind": kind, "cores": used, "what": what, "pairs": n_pairs}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # libraries (NCCL version banner, torchrun notices) print to fd 1: keep stdout clean for the JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,7 +179,7 @@ def main():
             tot_t += r["seconds"]; tot_tr += r["tracked"]; tot_f += r["features"]
         val = tot_tr / tot_t
         sample = "%d pairs x %d corners per step (bounded sample of the %d-pair workload), %s" % (args.cpu_sample_pairs, CORNERS, args.pairs, r["what"])
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int32 fixed-point + fp32 solve", "data": "synthetic", "config": cfg,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
@@ -337,7 +355,7 @@ def main():
             out["e2e"] = e2e
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
