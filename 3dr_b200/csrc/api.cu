@@ -81,6 +81,7 @@ PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
 // frame at every level, optionally level-0 copies (host-buffer entry points), and the point arrays.
 struct Workspace {
     DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs, pair_idx, al_prev, al_next, counter;
+    int epoch = 0;  // LK launches on this workspace (selects the work counter)
     void release()
     {
         pyr_prev.release(); pyr_next.release(); deriv.release(); lvl0_prev.release(); lvl0_next.release(); pts.release();
@@ -147,6 +148,7 @@ int check_lk_args(dr3lk_ctx* ctx, int w, int h, const LKArgs& a)
 int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, int pitch0,
                    size_t stride0, int batch, const PyrLayout& P, LKParams& lk)
 {
+    if (stride0 >= (1ull << 32) || P.der_ints[0] >= (1ull << 32)) return fail(ctx, DR3LK_E_SIZE, "images of 4 GiB or more are not supported");
     size_t pyr_bytes = 0, der_ints = 0;
     size_t lvl_off[kMaxLevels] = {0}, der_off[kMaxLevels] = {0};
     for (int l = 0; l <= P.ml; l++) {
@@ -166,16 +168,16 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         if (l == 0) {
             d.prev = prev0; d.next = next0;
             d.pitch_p = d.pitch_n = pitch0;
-            d.prev_stride = d.next_stride = (long long)stride0;
+            d.prev_stride = d.next_stride = (unsigned)stride0;
         } else {
             d.prev = (const uint8_t*)W.pyr_prev.p + lvl_off[l];
             d.next = (const uint8_t*)W.pyr_next.p + lvl_off[l];
             d.pitch_p = d.pitch_n = P.pitch[l];
-            d.prev_stride = d.next_stride = (long long)P.img_bytes[l];
+            d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
         }
         d.deriv = (const int*)W.deriv.p + der_off[l];
         d.dpitch = P.dpitch[l];
-        d.deriv_stride = (long long)P.der_ints[l];
+        d.deriv_stride = (unsigned)P.der_ints[l];
     }
     lk.max_level = P.ml;
 
@@ -183,13 +185,19 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = lk.lv[l];
         const bool down = l < P.ml;
-        uint8_t* dp = down ? const_cast<uint8_t*>(lk.lv[l + 1].prev) : nullptr;
-        uint8_t* dn = down ? const_cast<uint8_t*>(lk.lv[l + 1].next) : nullptr;
-        launch_pyr_level(L, s.prev, s.w, s.h, s.pitch_p, s.prev_stride, dp, down ? lk.lv[l + 1].pitch_p : 0,
-                         down ? lk.lv[l + 1].prev_stride : 0, const_cast<int*>(s.deriv), s.dpitch, s.deriv_stride, batch);
-        if (down)
-            launch_pyr_level(L, s.next, s.w, s.h, s.pitch_n, s.next_stride, dn, lk.lv[l + 1].pitch_n, lk.lv[l + 1].next_stride,
-                             nullptr, 0, 0, batch);
+        PyrLevelArgs a{};
+        a.prev_src = s.prev; a.next_src = s.next;
+        a.prev_src_stride = s.prev_stride; a.next_src_stride = s.next_stride;
+        a.w = s.w; a.h = s.h; a.src_pitch = s.pitch_p;
+        a.deriv = const_cast<int*>(s.deriv); a.dpitch = s.dpitch; a.deriv_stride = s.deriv_stride;
+        a.n_prev = batch; a.n_next = down ? batch : 0;
+        a.down = down;
+        if (down) {
+            a.prev_dst = const_cast<uint8_t*>(lk.lv[l + 1].prev); a.next_dst = const_cast<uint8_t*>(lk.lv[l + 1].next);
+            a.prev_dst_stride = lk.lv[l + 1].prev_stride; a.next_dst_stride = lk.lv[l + 1].next_stride;
+            a.dst_pitch = lk.lv[l + 1].pitch_p;
+        }
+        launch_pyr_level(L, a);
     }
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pyramid kernel launch");
@@ -209,10 +217,11 @@ void fill_lk_scalars(LKParams& lk, const LKArgs& a)
     lk.flags = a.flags;
 }
 
-int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk)
+int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk, Workspace& W)
 {
     Launch L{stream, cudaSuccess, 0};
-    if (!launch_lk_fast(L, lk)) launch_lk_generic(L, lk);
+    if (launch_lk_fast(L, lk)) W.epoch++;  // the persistent kernel consumed one work counter and re-armed the other
+    else launch_lk_generic(L, lk);
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "LK kernel launch");
     return DR3LK_OK;
@@ -265,8 +274,12 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     lk.batch = batch;
     lk.n_total = n_total;
     lk.fast_ok = aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride);
-    CU_TRY(ctx, W.counter.reserve(sizeof(int)));
+    if (!W.counter.p) {
+        CU_TRY(ctx, W.counter.reserve(2 * sizeof(int)));
+        CU_TRY(ctx, cudaMemsetAsync(W.counter.p, 0, 2 * sizeof(int), stream));
+    }
     lk.work_counter = (int*)W.counter.p;
+    lk.work_epoch = W.epoch;
     // point -> pair mapping: a division when every pair has the same number of points, else a lookup table
     bool uniform = n_total % batch == 0;
     for (int b = 0; uniform && b < batch; b++) uniform = (pts_offset[b + 1] - pts_offset[b]) == n_total / batch;
@@ -280,7 +293,7 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
         if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pair index kernel launch");
         lk.pair_idx = (const int*)W.pair_idx.p;
     }
-    rc = run_lk(ctx, stream, lk);
+    rc = run_lk(ctx, stream, lk, W);
     if (ctx->profiling) {
         CU_TRY(ctx, cudaEventRecord(pr.e[2], stream));
         ctx->prof.push_back(pr);
@@ -564,29 +577,33 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     Workspace& W = ctx->ws;
     const int pitch0 = align_up(w, 16);
     const size_t img_bytes = (size_t)pitch0 * h;
-    CU_TRY(ctx, W.lvl0_prev.reserve(img_bytes));
-    CU_TRY(ctx, W.lvl0_next.reserve(img_bytes));
-    // device point block: prev(8n) next(8n) err(4n) stats-less status(n) offsets(8)
-    const size_t o_prev = 0, o_next = 8 * (size_t)n, o_err = 16 * (size_t)n, o_status = 20 * (size_t)n;
-    const size_t pts_bytes = 21 * (size_t)n + 16;
-    CU_TRY(ctx, W.pts.reserve(pts_bytes));
-    CU_TRY(ctx, W.offs.reserve(2 * sizeof(int)));
-    uint8_t* dp = (uint8_t*)W.pts.p;
-    CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_prev.p, pitch0, prev, prev_step, w, h, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpy2DAsync(W.lvl0_next.p, pitch0, next, next_step, w, h, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpyAsync(dp + o_prev, prev_pts, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
-    if (flags & DR3LK_USE_INITIAL_FLOW)
-        CU_TRY(ctx, cudaMemcpyAsync(dp + o_next, next_pts, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    // One device block and one pinned mirror of it: [prev image][next image][prev_pts 8n][offsets 16][next_pts 8n][err 4n][status n].
+    // Inputs are packed on the host and cross PCIe as ONE copy; outputs come back as ONE copy (latency path of C1/C2).
+    const size_t n8 = align_up_sz(8 * (size_t)n, 16);
+    const size_t o_prev = 2 * img_bytes, o_offs = o_prev + n8, o_next = o_offs + 16, o_err = o_next + n8, o_status = o_err + align_up_sz(4 * (size_t)n, 16);
+    const size_t total = o_status + align_up_sz((size_t)n, 16);
+    CU_TRY(ctx, W.lvl0_prev.reserve(total));
+    CU_TRY(ctx, ctx->pinned.reserve(total));
+    uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    for (int y = 0; y < h; y++) {
+        memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
+        memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
+    }
+    memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
     const int offs[2] = {0, n};
-    CU_TRY(ctx, cudaMemcpyAsync(W.offs.p, offs, sizeof(offs), cudaMemcpyHostToDevice, st));
-    rc = track_batch_device(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_next.p, w, h, pitch0, img_bytes, 1,
-                            (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status, err ? (float*)(dp + o_err) : nullptr,
-                            offs, (const int*)W.offs.p, n, nullptr, a);
+    memcpy(hp + o_offs, offs, sizeof(offs));
+    size_t in_bytes = o_next;
+    if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(dp + o_prev), (float*)(dp + o_next),
+                            dp + o_status, err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
     if (rc != DR3LK_OK) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(next_pts, dp + o_next, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaMemcpyAsync(status, dp + o_status, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (err) CU_TRY(ctx, cudaMemcpyAsync(err, dp + o_err, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
+    memcpy(next_pts, hp + o_next, 8 * (size_t)n);
+    memcpy(status, hp + o_status, (size_t)n);
+    if (err) memcpy(err, hp + o_err, 4 * (size_t)n);
     return DR3LK_OK;
 }
 

@@ -15,9 +15,9 @@ struct LevelDesc {
     const uint8_t* prev;   // [batch][h][pitch_p]  level image of the previous frame
     const uint8_t* next;   // [batch][h][pitch_n]
     const int* deriv;      // [batch][h][dpitch]   Scharr (Ix, Iy) as packed int16x2, previous frame only
-    long long prev_stride; // bytes between consecutive pairs
-    long long next_stride;
-    long long deriv_stride;  // ints between consecutive pairs
+    unsigned prev_stride;  // bytes between consecutive pairs (< 4 GiB per image; pair * stride is a 32x32->64 multiply)
+    unsigned next_stride;
+    unsigned deriv_stride; // ints between consecutive pairs
     int pitch_p, pitch_n;    // bytes
     int dpitch;              // ints
     int w, h;
@@ -33,7 +33,8 @@ struct LKParams {
     const int* pair_idx;   // device, one frame-pair index per point (used when uniform_n == 0)
     int uniform_n;         // > 0: every pair has exactly this many points (pair = point / uniform_n)
     int fast_ok;           // all level images / derivatives are 16-B aligned (base, pitch, stride)
-    int* work_counter;     // device int, zeroed by the launcher: next point index for the persistent warps
+    int* work_counter;     // two device ints (zero-initialised): counter [work_epoch & 1] feeds the persistent warps of
+    int work_epoch;        // this launch, which also re-zeroes the other one for the next launch (no memset per call)
     float eps2_lo, eps2_hi; // fp32 brackets of eps2: below lo / above hi the fp32 estimate of |delta|^2 decides
     double eps2;           // criteria.epsilon^2
     double min_eig_thr;
@@ -53,10 +54,19 @@ struct Launch {
 };
 
 // pyramid.cu
-// One level step for `n_img` images: reads src level, writes (optionally) the 5-tap down-sampled next level and
-// (optionally) the Scharr derivative of the src level.
-void launch_pyr_level(Launch& L, const uint8_t* src, int w, int h, int src_pitch, long long src_stride, uint8_t* dst,
-                      int dst_pitch, long long dst_stride, int* deriv, int dpitch, long long deriv_stride, int n_img);
+// One level step: reads the source level of n_prev previous-frame images and n_next next-frame images (same size and
+// pitch), writes the 5-tap down-sampled next level of both (when `down`) and the Scharr derivative of the previous-frame
+// source level (when deriv != nullptr) -- one launch for both pyramids.
+struct PyrLevelArgs {
+    const uint8_t* prev_src; const uint8_t* next_src;
+    uint8_t* prev_dst; uint8_t* next_dst;
+    unsigned prev_src_stride, next_src_stride, prev_dst_stride, next_dst_stride;  // bytes between images
+    int* deriv; unsigned deriv_stride;  // ints between images
+    int w, h, src_pitch, dst_pitch, dpitch;
+    int n_prev, n_next;
+    bool down;
+};
+void launch_pyr_level(Launch& L, const PyrLevelArgs& a);
 void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
                      uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding);
 

@@ -328,16 +328,17 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         float fx, fy;
         if (!template_origin(pp, level, ipx, ipy, fx, fy)) return;
         const LevelDesc& L = P.lv[level];
-        T::stage_I(sI, L.prev + (long long)pair * L.prev_stride, L.pitch_p, L.w, L.h, ipx, ipy, lane);
-        T::stage_D(sD, L.deriv + (long long)pair * L.deriv_stride, L.dpitch, L.w, L.h, ipx, ipy, lane);
+        T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, L.w, L.h, ipx, ipy, lane);
+        T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, L.w, L.h, ipx, ipy, lane);
     };
     auto fetch = [&]() -> int {
         int f = 0;
-        if (lane == 0) f = atomicAdd(P.work_counter, 1);
+        if (lane == 0) f = atomicAdd(P.work_counter + (P.work_epoch & 1), 1);
         return __shfl_sync(0xffffffffu, f, 0);
     };
     auto pair_of = [&](int f) -> int { return P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f); };
 
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.work_counter[(P.work_epoch & 1) ^ 1] = 0;  // ready for the next launch
     int f = fetch();
     if (f >= P.n_total) return;
     float2 pp = P.prev_pts[f];
@@ -363,7 +364,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             const LevelDesc& L = P.lv[level];
             const int w = L.w, h = L.h;
             const float sc = __int_as_float((127 - level) << 23);
-            const uint8_t* imgJ = L.next + (long long)pair * L.next_stride;
+            const uint8_t* imgJ = L.next + (unsigned long long)(unsigned)pair * L.next_stride;
 
             int ipx, ipy;
             float px, py;
@@ -572,20 +573,18 @@ bool launch_one(Launch& L, const LKParams& p)
         if (p.lv[l].w < G::MIN_W || p.lv[l].h < G::MIN_H) return false;  // tiny level: lk_generic handles it
     const size_t smem = (size_t)G::WARPS * G::WARP_WORDS * sizeof(unsigned);
     L.err = cudaFuncSetAttribute(lk_fast_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (L.err != cudaSuccess) return true;
+    if (L.err != cudaSuccess) return false;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_fast_kernel<G>, G::WARPS * 32, smem);
-    if (L.err != cudaSuccess) return true;
+    if (L.err != cudaSuccess) return false;
     const int want = (p.n_total + G::WARPS - 1) / G::WARPS;
     const int blocks = std::min(want, std::max(1, per_sm) * sms);
-    L.err = cudaMemsetAsync(p.work_counter, 0, sizeof(int), L.stream);
-    if (L.err != cudaSuccess) return true;
     lk_fast_kernel<G><<<blocks, G::WARPS * 32, smem, L.stream>>>(p);
     L.err = cudaGetLastError();
     L.launches++;
-    return true;
+    return L.err == cudaSuccess;  // true: the persistent kernel ran and consumed its work counter
 }
 
 }  // namespace
@@ -598,7 +597,7 @@ bool lk_fast_supported(int win_w, int win_h)
 bool launch_lk_fast(Launch& L, const LKParams& p)
 {
     if (!lk_fast_supported(p.win_w, p.win_h) || !p.fast_ok) return false;
-    if (L.err != cudaSuccess || p.n_total <= 0) return true;
+    if (L.err != cudaSuccess || p.n_total <= 0) return false;  // nothing launched; the generic launcher is a no-op here too
     if (p.win_w == 21) return launch_one<Geo<21, 21, 7>>(L, p);
     if (p.win_w == 31) return launch_one<Geo<31, 31, 8>>(L, p);
     return launch_one<Geo<30, 30, 10>>(L, p);

@@ -99,9 +99,9 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
 
     for (int level = P.max_level; level >= 0; --level) {
         const LevelDesc& L = P.lv[level];
-        const uint8_t* imgI = L.prev + (long long)pair * L.prev_stride;
-        const uint8_t* imgJ = L.next + (long long)pair * L.next_stride;
-        const int* der = L.deriv + (long long)pair * L.deriv_stride;
+        const uint8_t* imgI = L.prev + (unsigned long long)(unsigned)pair * L.prev_stride;
+        const uint8_t* imgJ = L.next + (unsigned long long)(unsigned)pair * L.next_stride;
+        const int* der = L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride;
         const int w = L.w, h = L.h;
         const float sc = __int_as_float((127 - level) << 23);  // (float)(1./(1 << level))
 

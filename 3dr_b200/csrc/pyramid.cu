@@ -26,22 +26,32 @@ __device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8
 // One pyramid level for a batch of images.  The source tile is staged once with 16-byte row-coalesced loads (interior
 // tiles of 16-B aligned images) or byte-wise with REFLECT_101 index reflection (edge tiles / unaligned sources); the
 // next Gaussian level (pyrDown) and the Scharr derivative of the source level are both produced from that tile.
-template <bool DOWN, bool DERIV>
+// blockIdx.z walks two image sets back to back: n_a "A" images (the previous frames: derivative + optional down-sample)
+// followed by the "B" images (the next frames: down-sample only), so one launch per level serves both pyramids.
+struct PyrSet {
+    const uint8_t* src;
+    uint8_t* dst;
+    unsigned src_stride, dst_stride;  // bytes between images
+};
+
+template <bool DOWN>
 __global__ void __launch_bounds__(PYR_THREADS)
-pyr_level_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, long long src_stride, int src_aligned,
-                 uint8_t* __restrict__ dst, int dst_pitch, long long dst_stride, int* __restrict__ deriv, int dpitch,
-                 long long deriv_stride)
+pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int src_aligned, int dst_pitch, int* __restrict__ deriv,
+                 int dpitch, unsigned deriv_stride)
 {
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
     __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
 
     const int tid = threadIdx.x;
-    const int img = blockIdx.z;
+    const bool set_b = (int)blockIdx.z >= n_a;
+    const int img = set_b ? blockIdx.z - n_a : blockIdx.z;
+    const PyrSet& S = set_b ? B : A;
+    const bool DERIV = !set_b && deriv != nullptr;
     const int xs = blockIdx.x * (2 * TOX);      // first source column this tile produces derivatives for
     const int ys = blockIdx.y * (2 * TOY);
     const int x0 = xs - HX;                     // source coordinate of tile[0][0]
     const int y0 = ys - 2;
-    const uint8_t* s = src + (long long)img * src_stride;
+    const uint8_t* s = S.src + (unsigned long long)(unsigned)img * S.src_stride;
 
     // columns xs-2 .. xs+2*TOX+1 are needed; the vector path also requires the 16-byte chunks to stay inside the row
     const bool xin = src_aligned && blockIdx.x >= 1 && xs + 2 * TOX + 2 <= w && x0 + SW <= src_pitch;
@@ -64,7 +74,7 @@ pyr_level_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, l
     if (DERIV) {
         // 4 consecutive pixels per thread: source (xs + 4g .. +3, ys + ly) <-> tile[ly + 2][HX + 4g ..]
         const int g = tid & 31;
-        int* d = deriv + (long long)img * deriv_stride;
+        int* d = deriv + (unsigned long long)(unsigned)img * deriv_stride;
         for (int ly = tid >> 5; ly < 2 * TOY; ly += PYR_THREADS / 32) {
             const int sx = xs + 4 * g, sy = ys + ly;
             if (sx < w && sy < h) {
@@ -117,7 +127,7 @@ pyr_level_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, l
         }
         __syncthreads();
         const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
-        uint8_t* o = dst + (long long)img * dst_stride;
+        uint8_t* o = S.dst + (unsigned long long)(unsigned)img * S.dst_stride;
         const int q = tid & 15, oy = tid >> 4;   // 4 outputs per thread, 16 threads per row, 16 rows
         const int gx = blockIdx.x * TOX + 4 * q, gy = blockIdx.y * TOY + oy;
         if (gx < dw && gy < dh) {
@@ -165,23 +175,20 @@ box_half_kernel(const uint8_t* __restrict__ src, int out_w, int out_h, long long
 
 }  // namespace
 
-void launch_pyr_level(Launch& L, const uint8_t* src, int w, int h, int src_pitch, long long src_stride, uint8_t* dst,
-                      int dst_pitch, long long dst_stride, int* deriv, int dpitch, long long deriv_stride, int n_img)
+void launch_pyr_level(Launch& L, const PyrLevelArgs& a)
 {
-    if (L.err != cudaSuccess || n_img <= 0) return;
-    dim3 grid((w + 2 * TOX - 1) / (2 * TOX), (h + 2 * TOY - 1) / (2 * TOY), n_img);
-    const int aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_stride) & 15) == 0;
-    if (dst && deriv)
-        pyr_level_kernel<true, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, dst, dst_pitch,
-                                                                       dst_stride, deriv, dpitch, deriv_stride);
-    else if (dst)
-        pyr_level_kernel<true, false><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, dst, dst_pitch,
-                                                                        dst_stride, nullptr, 0, 0);
-    else if (deriv)
-        pyr_level_kernel<false, true><<<grid, PYR_THREADS, 0, L.stream>>>(src, w, h, src_pitch, src_stride, aligned, nullptr, 0, 0,
-                                                                        deriv, dpitch, deriv_stride);
+    if (L.err != cudaSuccess || a.n_prev + a.n_next <= 0) return;
+    dim3 grid((a.w + 2 * TOX - 1) / (2 * TOX), (a.h + 2 * TOY - 1) / (2 * TOY), a.n_prev + a.n_next);
+    auto al = [](const void* p, size_t x, size_t y) { return ((reinterpret_cast<uintptr_t>(p) | x | y) & 15) == 0; };
+    const int aligned = al(a.prev_src, a.src_pitch, a.prev_src_stride) && (a.n_next == 0 || al(a.next_src, a.src_pitch, a.next_src_stride));
+    PyrSet A{a.prev_src, a.prev_dst, a.prev_src_stride, a.prev_dst_stride};
+    PyrSet B{a.next_src, a.next_dst, a.next_src_stride, a.next_dst_stride};
+    if (a.down)
+        pyr_level_kernel<true><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
+                                                                 a.deriv_stride);
     else
-        return;
+        pyr_level_kernel<false><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
+                                                                  a.deriv_stride);
     L.err = cudaGetLastError();
     L.launches++;
 }

@@ -176,3 +176,36 @@ def test_properties_full_size_synthetic(ctx, dr3):
     n = len(pts)
     assert np.array_equal(bp[:n].view(np.uint32), p.view(np.uint32)) and np.array_equal(bp[2 * n:].view(np.uint32), p.view(np.uint32))
     assert np.array_equal(bs[:n], s) and np.array_equal(be[2 * n:], e) and np.abs(bp[n:2 * n] - pts).max() < 1e-3
+
+
+def test_c5_semidense_lattice_bit_exact(ctx):
+    """C5: 4-px lattice (310 x 94 = 29140 points) on a 1241x376 synthetic pair -- many texture-less points, exercises the
+    minEig rejection path and status parity at full size."""
+    from tools import synth
+    a, b, _ = synth.make_pair(1007)
+    pts = synth.lattice(1241, 376)
+    assert len(pts) == 29140
+    got = ctx.calc_optical_flow_pyr_lk(a, b, pts)
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts)
+    _assert_bit_exact(got, exp, "c5")
+    # flat images: every lattice point is rejected by the min-eigenvalue test
+    flat = np.full((376, 1241), 77, np.uint8)
+    p, s, e = ctx.calc_optical_flow_pyr_lk(flat, flat, pts)
+    assert not s.any() and not e.any()
+
+
+def test_c4_4k_31x31_five_levels_bit_exact(ctx):
+    """C4: 3840x2160, 31x31 window, maxLevel 4 (5 levels, none dropped), corners from goodFeaturesToTrack."""
+    from tools import synth
+    a, b, M = synth.make_pair(2000, 3840, 2160)
+    pts = synth.corners(a, 3000, 5)
+    got = ctx.calc_optical_flow_pyr_lk(a, b, pts, None, (31, 31), 4, (3, 30, 0.01), 0)
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, (31, 31), 4, (3, 30, 0.01), 0)
+    _assert_bit_exact(got, exp, "c4")
+    gt = pts @ M[:, :2].T.astype(np.float32) + M[:, 2].astype(np.float32)
+    d = np.linalg.norm(got[0] - gt, axis=1)[got[1] == 1]
+    assert got[1].mean() > 0.98 and np.median(d) < 0.1
+    # the box pyramid of a 3840-wide frame takes the SSE2 rounding path on x86 (3840 % 16 == 0), SURVEY.md 8d
+    box = ctx.box_pyramid(a, 3)
+    exp_box = oracle.box_pyramid(a, 3)
+    assert all(np.array_equal(x, y) for x, y in zip(box[1:], exp_box[1:]))

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Informational numbers for the BASELINE.json configs that are not the bench.py headline (C1, C2, C4, C5):
+single-call latency through the host-buffer C ABI and batched device-resident throughput, next to cv2 on the host.
+Run on the GPU box:  python tools/bench_configs.py > gpurun_out/configs.json"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+from _common import golden_case, load_gray  # noqa: E402
+from oracle import cv2_ref  # noqa: E402
+from tools import synth  # noqa: E402
+
+dr3 = importlib.import_module("3dr_b200")
+ctx = dr3.Context(0)
+out = {}
+
+
+def time_call(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def cpu_time(a, b, pts, win, ml, crit, flags=0, init=None, n=5):
+    return time_call(lambda: cv2_ref.calc_optical_flow_pyr_lk(a, b, pts, init, win, ml, crit, flags), n=n, warm=1)
+
+
+# ---- C1: kitti0 -> kitti1, FAST corners; default and the reference's literal parameters
+a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+pts = golden_case("c1_default_21x21")["prev_pts"][:4607]
+for name, (win, ml, crit, flags) in {"c1_21x21": ((21, 21), 3, (3, 30, 0.01), 0), "c1_reference_30x30": ((30, 30), 4, (3, 1000, 1e-3), 4)}.items():
+    init = pts.copy() if flags & 4 else None
+    t = time_call(lambda: ctx.calc_optical_flow_pyr_lk(a, b, pts, init, win, ml, crit, flags))
+    p, s, e = ctx.calc_optical_flow_pyr_lk(a, b, pts, init, win, ml, crit, flags)
+    tc = cpu_time(a, b, pts, win, ml, crit, flags, init)
+    out[name] = {"points": len(pts), "tracked": int(s.sum()), "gpu_call_ms": 1e3 * t, "gpu_features_per_s": len(pts) / t,
+                 "cv2_call_ms": 1e3 * tc, "cv2_features_per_s": len(pts) / tc, "cv2_threads": cv2_ref.cv2.getNumThreads()}
+
+# ---- C2: kitti0..9 frame-to-frame chain (9 dependent calls)
+frames = [load_gray("kitti%d.png" % i) for i in range(10)]
+
+
+def chain(track):
+    cur, surv = pts, []
+    for i in range(9):
+        p, s, _ = track(frames[i], frames[i + 1], cur)
+        cur = p[s == 1]; surv.append(len(cur))
+    return surv
+
+
+t = time_call(lambda: chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c)), n=10)
+tc = time_call(lambda: chain(lambda x, y, c: cv2_ref.calc_optical_flow_pyr_lk(x, y, c)), n=3, warm=1)
+out["c2_chain"] = {"survivors": chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c)), "gpu_chain_ms": 1e3 * t, "cv2_chain_ms": 1e3 * tc}
+
+
+def device_batch(prev, nxt, pts_list, win, ml, crit, reps=3):
+    B, h, w = prev.shape
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pts_list])]).astype(np.int32)
+    allp = np.concatenate(pts_list).astype(np.float32)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        dp, dn = torch.from_numpy(prev).cuda(), torch.from_numpy(nxt).cuda()
+        dpts = torch.from_numpy(allp).cuda(); dnext = torch.zeros_like(dpts)
+        dst = torch.zeros(len(allp), dtype=torch.uint8, device="cuda"); derr = torch.zeros(len(allp), device="cuda")
+        ctx.set_stream(st.cuda_stream)
+        run = lambda: ctx.track_batch(dp.data_ptr(), dn.data_ptr(), w, h, w, h * w, B, dpts.data_ptr(), dnext.data_ptr(), dst.data_ptr(),
+                                      derr.data_ptr(), offs, None, win, ml, crit, 0)
+        run(); run(); st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            run()
+        e1.record(st); st.synchronize()
+        ctx.set_stream(None)
+        return e0.elapsed_time(e1) / reps * 1e-3, int(dst.sum().item()), len(allp)
+
+
+# ---- C4: 3840x2160, 50k corners, 31x31, 5 levels; batch of 8 pairs
+a4, b4, _ = synth.make_pair(2000, 3840, 2160)
+p4 = synth.corners(a4, 50000, 5)
+t, tracked, n = device_batch(np.stack([a4] * 8), np.stack([b4] * 8), [p4] * 8, (31, 31), 4, (3, 30, 0.01))
+tc = cpu_time(a4, b4, p4, (31, 31), 4, (3, 30, 0.01), n=3)
+out["c4_4k_31x31"] = {"pairs": 8, "points_per_pair": len(p4), "gpu_features_per_s": n / t, "gpu_ms_per_pair": 1e3 * t / 8,
+                      "cv2_features_per_s": len(p4) / tc, "cv2_ms_per_pair": 1e3 * tc}
+
+# ---- C5: semi-dense lattice on 1241x376, batch of 256 pairs
+a5, b5, _ = synth.make_pair(1000)
+p5 = synth.lattice(1241, 376)
+t, tracked, n = device_batch(np.stack([a5] * 256), np.stack([b5] * 256), [p5] * 256, (21, 21), 3, (3, 30, 0.01))
+tc = cpu_time(a5, b5, p5, (21, 21), 3, (3, 30, 0.01), n=3)
+out["c5_semidense"] = {"pairs": 256, "points_per_pair": len(p5), "tracked_fraction": tracked / n, "gpu_features_per_s": n / t,
+                       "cv2_features_per_s": len(p5) / tc}
+out["host"] = {"cpus": os.cpu_count(), "cv2": cv2_ref.CV2_VERSION, "gpu": torch.cuda.get_device_name(0)}
+print(json.dumps(out, indent=1))

@@ -57,3 +57,16 @@ for n in [p[0] for p in phases] + ['other']:
         top = sorted(ops[n].items(), key=lambda kv: -kv[1])[:9]
         print('%-28s %9.1f %6.1f%%   %s' % (n, tot[n], 100 * stall[n] / max(ts, 1), ' '.join('%s:%.0f' % (o, v) for o, v in top)))
 print('%-28s %9.1f' % ('TOTAL', sum(tot.values())))
+if os.environ.get('DUMP_PHASE'):
+    want = os.environ['DUMP_PHASE']
+    for k in range(len(ins)):
+        inner, outer = lines[k][0] if lines[k][0] else ((None, 0), (None, 0))
+        ph = 'other'
+        if outer[0] == srcfile:
+            for n, a, b in phases:
+                if a <= outer[1] < b:
+                    ph = n; break
+        if ph == want:
+            ie = int(ins[k][ci['Instructions Executed']] or 0) / nfeat
+            st = int(ins[k][ci['Warp Stall Sampling (All Samples)']] or 0)
+            print('%5d %6.2f %6d  %-18s %-14s %s' % (k, ie, st, '%s:%d' % (inner[0][:12] if inner[0] else '?', inner[1]), 'at:%d' % outer[1], lines[k][1][:90]))
