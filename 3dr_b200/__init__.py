@@ -31,7 +31,8 @@ SYMBOLS = [
     "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
     "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
-    "dr3lk_build_lk_pyramid",
+    "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
+    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks",
 ]
 
 
@@ -84,6 +85,13 @@ def lib():
     L.dr3lk_lk_level_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, P(c_int), P(c_int)]
     L.dr3lk_build_lk_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, P(c_void_p),
                                          P(c_void_p), P(c_int)]
+    L.dr3lk_pyramid_create.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, P(c_void_p)]
+    L.dr3lk_pyramid_destroy.argtypes = [c_void_p]
+    L.dr3lk_pyramid_destroy.restype = None
+    L.dr3lk_pyramid_levels.argtypes = [c_void_p]
+    L.dr3lk_calc_optical_flow_pyr_lk_cached.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
+    L.dr3lk_filter_tracks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, P(c_int)]
     _lib = L
     return L
 
@@ -240,6 +248,44 @@ class Context:
             criteria[0], criteria[1], float(criteria[2]), flags, float(min_eig_threshold)))
         return npts, status, err
 
+    def calc_optical_flow_pyr_lk_cached(self, prev_pyr, next_pyr, prev_pts, next_pts=None, max_level=3,
+                                        criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4, want_err=True):
+        """calc_optical_flow_pyr_lk on two prebuilt `Pyramid`s (no image upload, no pyramid build)."""
+        pp = np.ascontiguousarray(np.asarray(prev_pts, np.float32).reshape(-1, 2))
+        n = pp.shape[0]
+        if flags & USE_INITIAL_FLOW:
+            npts = np.ascontiguousarray(np.asarray(next_pts, np.float32).reshape(-1, 2)).copy()
+            if npts.shape[0] != n:
+                raise Dr3lkError(E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints")
+        else:
+            npts = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32) if want_err else None
+        win = prev_pyr.win
+        self._check(lib().dr3lk_calc_optical_flow_pyr_lk_cached(
+            self._h, prev_pyr._h, next_pyr._h, pp.ctypes.data, npts.ctypes.data, status.ctypes.data,
+            err.ctypes.data if want_err else None, n, win[0], win[1], max_level, criteria[0], criteria[1], float(criteria[2]), flags,
+            float(min_eig_threshold)))
+        return npts, status, err
+
+    def filter_tracks(self, ref_pts, cur_pts, status, fx=None, fy=None, cx=0.0, cy=0.0):
+        """Reference src/initialization.cpp:615-635: drop status == 0 (order kept), disparity norms and, when a pinhole
+        (fx, fy, cx, cy) is given, unit bearing vectors of the current points. Returns (ref, cur, disparity, bearing|None)."""
+        r = np.ascontiguousarray(np.asarray(ref_pts, np.float32).reshape(-1, 2))
+        c = np.ascontiguousarray(np.asarray(cur_pts, np.float32).reshape(-1, 2))
+        st = np.ascontiguousarray(np.asarray(status, np.uint8))
+        n = r.shape[0]
+        assert c.shape[0] == n and st.shape[0] == n
+        o_r, o_c = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32)
+        disp = np.zeros(n, np.float64)
+        bear = np.zeros((n, 3), np.float64) if fx is not None else None
+        k = ctypes.c_int(0)
+        self._check(lib().dr3lk_filter_tracks(self._h, r.ctypes.data, c.ctypes.data, st.ctypes.data, n, float(fx or 1.0), float(fy or 1.0),
+                                              float(cx), float(cy), o_r.ctypes.data, o_c.ctypes.data, disp.ctypes.data,
+                                              bear.ctypes.data if bear is not None else None, ctypes.byref(k)))
+        k = k.value
+        return o_r[:k], o_c[:k], disp[:k], (bear[:k] if bear is not None else None)
+
     def track_batch(self, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,
                     err_ptr, pts_offset, stats_ptr=None, win=(21, 21), max_level=3,
                     criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4):
@@ -279,6 +325,33 @@ class Context:
             stats.ctypes.data if stats is not None else None, chunk_pairs, win[0], win[1], max_level, criteria[0],
             criteria[1], float(criteria[2]), flags, float(min_eig_threshold)))
         return npts, status, err, stats
+
+
+class Pyramid:
+    """Device-resident LK pyramid of one frame (Gaussian levels + Scharr derivatives), SURVEY.md 8(f-2)."""
+
+    def __init__(self, ctx, img, win=(21, 21), max_level=3):
+        img0 = _gray(img)
+        h, w = img0.shape
+        self._h = ctypes.c_void_p()
+        self.ctx, self.win, self.shape = ctx, tuple(win), (h, w)
+        ctx._check(lib().dr3lk_pyramid_create(ctx._h, img0.ctypes.data, w, h, img0.strides[0], win[0], win[1], max_level,
+                                              ctypes.byref(self._h)))
+
+    @property
+    def levels(self):
+        return lib().dr3lk_pyramid_levels(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dr3lk_pyramid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decode_stats(stats):

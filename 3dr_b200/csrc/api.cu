@@ -227,6 +227,41 @@ int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk, Workspace& W
     return DR3LK_OK;
 }
 
+// LK over level descriptors that are already filled in (lk.lv[0..max_level], lk.max_level, lk.fast_ok).
+int run_tracking(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, LKParams& lk, int batch, const float* prev_pts_dev,
+                 float* next_pts_dev, uint8_t* status_dev, float* err_dev, const int* pts_offset, const int* pts_offset_dev, int n_total,
+                 uint32_t* stats_dev, const LKArgs& a)
+{
+    fill_lk_scalars(lk, a);
+    lk.prev_pts = (const float2*)prev_pts_dev;
+    lk.next_pts = (float2*)next_pts_dev;
+    lk.status = status_dev;
+    lk.err = err_dev;
+    lk.stats = stats_dev;
+    lk.batch = batch;
+    lk.n_total = n_total;
+    if (!W.counter.p) {
+        CU_TRY(ctx, W.counter.reserve(2 * sizeof(int)));
+        CU_TRY(ctx, cudaMemsetAsync(W.counter.p, 0, 2 * sizeof(int), stream));
+    }
+    lk.work_counter = (int*)W.counter.p;
+    lk.work_epoch = W.epoch;
+    // point -> pair mapping: a division when every pair has the same number of points, else a lookup table
+    bool uniform = n_total % batch == 0;
+    for (int b = 0; uniform && b < batch; b++) uniform = (pts_offset[b + 1] - pts_offset[b]) == n_total / batch;
+    if (uniform) {
+        lk.uniform_n = n_total / batch;
+    } else {
+        CU_TRY(ctx, W.pair_idx.reserve(sizeof(int) * (size_t)n_total));
+        Launch L{stream, cudaSuccess, 0};
+        launch_pair_index(L, pts_offset_dev, batch, n_total, (int*)W.pair_idx.p);
+        ctx->launches += L.launches;
+        if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pair index kernel launch");
+        lk.pair_idx = (const int*)W.pair_idx.p;
+    }
+    return run_lk(ctx, stream, lk, W);
+}
+
 // Device-resident batch on (W, stream).  pts_offset: host offsets, pts_offset_dev: device copy of the same.
 int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev_dev, const uint8_t* next_dev, int w,
                        int h, size_t pitch, size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev,
@@ -265,35 +300,9 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, (int)pitch, image_stride, batch, P, lk);
     if (rc != DR3LK_OK) return rc;
     if (ctx->profiling) CU_TRY(ctx, cudaEventRecord(pr.e[1], stream));
-    fill_lk_scalars(lk, a);
-    lk.prev_pts = (const float2*)prev_pts_dev;
-    lk.next_pts = (float2*)next_pts_dev;
-    lk.status = status_dev;
-    lk.err = err_dev;
-    lk.stats = stats_dev;
-    lk.batch = batch;
-    lk.n_total = n_total;
     lk.fast_ok = aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride);
-    if (!W.counter.p) {
-        CU_TRY(ctx, W.counter.reserve(2 * sizeof(int)));
-        CU_TRY(ctx, cudaMemsetAsync(W.counter.p, 0, 2 * sizeof(int), stream));
-    }
-    lk.work_counter = (int*)W.counter.p;
-    lk.work_epoch = W.epoch;
-    // point -> pair mapping: a division when every pair has the same number of points, else a lookup table
-    bool uniform = n_total % batch == 0;
-    for (int b = 0; uniform && b < batch; b++) uniform = (pts_offset[b + 1] - pts_offset[b]) == n_total / batch;
-    if (uniform) {
-        lk.uniform_n = n_total / batch;
-    } else {
-        CU_TRY(ctx, W.pair_idx.reserve(sizeof(int) * (size_t)n_total));
-        Launch L{stream, cudaSuccess, 0};
-        launch_pair_index(L, pts_offset_dev, batch, n_total, (int*)W.pair_idx.p);
-        ctx->launches += L.launches;
-        if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pair index kernel launch");
-        lk.pair_idx = (const int*)W.pair_idx.p;
-    }
-    rc = run_lk(ctx, stream, lk, W);
+    rc = run_tracking(ctx, W, stream, lk, batch, prev_pts_dev, next_pts_dev, status_dev, err_dev, pts_offset, pts_offset_dev, n_total,
+                      stats_dev, a);
     if (ctx->profiling) {
         CU_TRY(ctx, cudaEventRecord(pr.e[2], stream));
         ctx->prof.push_back(pr);
@@ -721,6 +730,183 @@ int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, siz
     }
     CU_TRY(ctx, cudaStreamSynchronize(st));
     if (eff_max_level) *eff_max_level = P.ml;
+    return DR3LK_OK;
+}
+
+
+/* ---------------------------------------------------------------------------------------------- */
+/* f-2: cached pyramids                                                                            */
+/* ---------------------------------------------------------------------------------------------- */
+
+struct dr3lk_pyramid {
+    dr3lk_ctx* ctx;
+    int w, h, win_w, win_h;
+    PyrLayout P;
+    DevBuf img, deriv;
+    LevelDesc lv[kMaxLevels];  // prev / deriv fields describe this frame
+};
+
+int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h, int max_level,
+                         dr3lk_pyramid** out)
+{
+    if (!ctx || !out) return DR3LK_E_ARG;
+    *out = nullptr;
+    LKArgs a{win_w, win_h, max_level, 0, 0, 0, 0., 0.};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (!img || step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "pyramid_create: bad image arguments");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    dr3lk_pyramid* p = new (std::nothrow) dr3lk_pyramid();
+    if (!p) return fail(ctx, DR3LK_E_CUDA, "out of host memory");
+    p->ctx = ctx; p->w = w; p->h = h; p->win_w = win_w; p->win_h = win_h;
+    p->P = make_layout(w, h, win_w, win_h, max_level);
+    const PyrLayout& P = p->P;
+    size_t img_total = 0, der_total = 0, ioff[kMaxLevels], doff[kMaxLevels];
+    for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
+    cudaError_t e = p->img.reserve(img_total);
+    if (e == cudaSuccess) e = p->deriv.reserve(der_total * sizeof(int));
+    if (e == cudaSuccess) e = ctx->pinned.reserve(P.img_bytes[0]);
+    if (e != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, e, "pyramid_create: allocation"); }
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * P.pitch[0], img + (size_t)y * step, (size_t)w);
+    e = cudaMemcpyAsync(p->img.p, hp, P.img_bytes[0], cudaMemcpyHostToDevice, st);
+    Launch L{st, e, 0};
+    for (int l = 0; l <= P.ml; l++) {
+        LevelDesc& d = p->lv[l];
+        d.w = P.w[l]; d.h = P.h[l];
+        d.prev = d.next = (const uint8_t*)p->img.p + ioff[l];
+        d.pitch_p = d.pitch_n = P.pitch[l];
+        d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
+        d.deriv = (const int*)p->deriv.p + doff[l];
+        d.dpitch = P.dpitch[l];
+        d.deriv_stride = (unsigned)P.der_ints[l];
+    }
+    for (int l = 0; l <= P.ml; l++) {
+        const LevelDesc& s = p->lv[l];
+        PyrLevelArgs pa{};
+        pa.prev_src = s.prev; pa.prev_src_stride = s.prev_stride;
+        pa.w = s.w; pa.h = s.h; pa.src_pitch = s.pitch_p;
+        pa.deriv = const_cast<int*>(s.deriv); pa.dpitch = s.dpitch; pa.deriv_stride = s.deriv_stride;
+        pa.n_prev = 1; pa.n_next = 0;
+        pa.down = l < P.ml;
+        if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
+        launch_pyr_level(L, pa);
+    }
+    ctx->launches += L.launches;
+    // the pinned staging buffer is reused by the next call: wait for the upload
+    if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st);
+    if (L.err != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, L.err, "pyramid_create"); }
+    *out = p;
+    return DR3LK_OK;
+}
+
+void dr3lk_pyramid_destroy(dr3lk_pyramid* pyr)
+{
+    if (!pyr) return;
+    cudaSetDevice(pyr->ctx->device);
+    pyr->img.release();
+    pyr->deriv.release();
+    delete pyr;
+}
+
+int dr3lk_pyramid_levels(const dr3lk_pyramid* pyr) { return pyr ? pyr->P.ml + 1 : 0; }
+
+int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const dr3lk_pyramid* next, const float* prev_pts,
+                                          float* next_pts, uint8_t* status, float* err, int n, int win_w, int win_h, int max_level,
+                                          int crit_type, int crit_max_count, double crit_eps, int flags, double min_eig_threshold)
+{
+    if (!ctx || !prev || !next) return DR3LK_E_ARG;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    int rc = check_lk_args(ctx, prev->w, prev->h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (prev->ctx != ctx || next->ctx != ctx) return fail(ctx, DR3LK_E_ARG, "pyramids belong to another context");
+    if (prev->w != next->w || prev->h != next->h)
+        return fail(ctx, DR3LK_E_SIZE, "(-215:Assertion failed) prevPyr[level * lvlStep1].size() == nextPyr[level * lvlStep2].size()");
+    if (prev->win_w != win_w || prev->win_h != win_h || next->win_w != win_w || next->win_h != win_h)
+        return fail(ctx, DR3LK_E_ARG, "pyramids were built for another window size");
+    if (n < 0) return fail(ctx, DR3LK_E_ARG, "negative point count");
+    if (n == 0) return DR3LK_OK;
+    if (!prev_pts || !next_pts || !status) return fail(ctx, DR3LK_E_ARG, "null point / status buffer");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    LKParams lk;
+    memset(&lk, 0, sizeof(lk));
+    const int ml = std::min(std::min(prev->P.ml, next->P.ml), max_level);
+    for (int l = 0; l <= ml; l++) {
+        lk.lv[l] = prev->lv[l];
+        lk.lv[l].next = next->lv[l].prev;
+        lk.lv[l].pitch_n = next->lv[l].pitch_p;
+        lk.lv[l].next_stride = next->lv[l].prev_stride;
+    }
+    lk.max_level = ml;
+    lk.fast_ok = 1;  // pyramid buffers are always 16-B aligned
+    const size_t n8 = align_up_sz(8 * (size_t)n, 16);
+    const size_t o_prev = 0, o_offs = n8, o_next = o_offs + 16, o_err = o_next + n8, o_status = o_err + align_up_sz(4 * (size_t)n, 16);
+    const size_t total = o_status + align_up_sz((size_t)n, 16);
+    CU_TRY(ctx, W.pts.reserve(total));
+    CU_TRY(ctx, ctx->pinned.reserve(total));
+    uint8_t* dp = (uint8_t*)W.pts.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
+    const int offs[2] = {0, n};
+    memcpy(hp + o_offs, offs, sizeof(offs));
+    size_t in_bytes = o_next;
+    if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status,
+                      err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
+    if (rc != DR3LK_OK) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    memcpy(next_pts, hp + o_next, 8 * (size_t)n);
+    memcpy(status, hp + o_status, (size_t)n);
+    if (err) memcpy(err, hp + o_err, 4 * (size_t)n);
+    return DR3LK_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* f-3: status filter + disparity + bearing vectors                                                */
+/* ---------------------------------------------------------------------------------------------- */
+
+int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_pts, const uint8_t* status, int n, double fx, double fy,
+                        double cx, double cy, float* out_ref, float* out_cur, double* out_disparity, double* out_bearing, int* n_kept)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (n < 0 || !n_kept) return fail(ctx, DR3LK_E_ARG, "filter_tracks: bad argument");
+    *n_kept = 0;
+    if (n == 0) return DR3LK_OK;
+    if (!ref_pts || !cur_pts || !status || !out_ref || !out_cur || !out_disparity) return fail(ctx, DR3LK_E_ARG, "filter_tracks: null buffer");
+    if (out_bearing && (fx == 0.0 || fy == 0.0)) return fail(ctx, DR3LK_E_ARG, "filter_tracks: zero focal length");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    // [ref 8n][cur 8n][status n (pad 16)] in; [out_ref 8n][out_cur 8n][disp 8n][bearing 24n][count 16] out
+    const size_t n8 = align_up_sz(8 * (size_t)n, 16), n1 = align_up_sz((size_t)n, 16), n24 = align_up_sz(24 * (size_t)n, 16);
+    const size_t i_ref = 0, i_cur = n8, i_st = 2 * n8, o_ref = i_st + n1, o_cur = o_ref + n8, o_disp = o_cur + n8, o_bear = o_disp + n8,
+                 o_cnt = o_bear + n24, total = o_cnt + 16;
+    CU_TRY(ctx, W.pts.reserve(total));
+    CU_TRY(ctx, ctx->pinned.reserve(total));
+    uint8_t* dp = (uint8_t*)W.pts.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    memcpy(hp + i_ref, ref_pts, 8 * (size_t)n);
+    memcpy(hp + i_cur, cur_pts, 8 * (size_t)n);
+    memcpy(hp + i_st, status, (size_t)n);
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, o_ref, cudaMemcpyHostToDevice, st));
+    Launch L{st, cudaSuccess, 0};
+    launch_filter_tracks(L, (const float*)(dp + i_ref), (const float*)(dp + i_cur), dp + i_st, n, fx, fy, cx, cy, (float*)(dp + o_ref),
+                         (float*)(dp + o_cur), (double*)(dp + o_disp), out_bearing ? (double*)(dp + o_bear) : nullptr, (int*)(dp + o_cnt));
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "filter kernel launch");
+    CU_TRY(ctx, cudaMemcpyAsync(hp + o_ref, dp + o_ref, total - o_ref, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    const int k = *reinterpret_cast<const int*>(hp + o_cnt);
+    *n_kept = k;
+    memcpy(out_ref, hp + o_ref, 8 * (size_t)k);
+    memcpy(out_cur, hp + o_cur, 8 * (size_t)k);
+    memcpy(out_disparity, hp + o_disp, 8 * (size_t)k);
+    if (out_bearing) memcpy(out_bearing, hp + o_bear, 24 * (size_t)k);
     return DR3LK_OK;
 }
 

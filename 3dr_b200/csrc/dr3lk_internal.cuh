@@ -70,6 +70,10 @@ void launch_pyr_level(Launch& L, const PyrLevelArgs& a);
 void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
                      uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding);
 
+// filter.cu
+void launch_filter_tracks(Launch& L, const float* ref, const float* cur, const uint8_t* status, int n, double fx, double fy, double cx,
+                          double cy, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept);
+
 // lk_generic.cu
 void launch_lk_generic(Launch& L, const LKParams& p);
 void launch_pair_index(Launch& L, const int* pts_offset_dev, int batch, int n_total, int* pair_idx_dev);

@@ -119,6 +119,34 @@ int dr3lk_lk_level_sizes(int w, int h, int win_w, int win_h, int max_level, int*
 int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h,
                            int max_level, uint8_t* const* out_levels, int16_t* const* out_derivs, int* eff_max_level);
 
+/* ---- SURVEY.md 8(f) "next" rows ---------------------------------------------------------------------------- */
+
+/* f-2: pyramid caching.  The reference passes only level-0 images to cv::calcOpticalFlowPyrLK
+ * (src/initialization.cpp:608-609), so OpenCV rebuilds both Gaussian pyramids and the reference frame's Scharr
+ * derivatives on every call -- also on every retry against the same reference frame (src/handler.cpp:67-72).
+ * A dr3lk_pyramid is the device-resident equivalent of OpenCV's precomputed-pyramid input form: Gaussian levels
+ * (with OpenCV's early stop for win/max_level) plus Scharr derivatives, built once per frame. */
+typedef struct dr3lk_pyramid dr3lk_pyramid;
+int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h, int max_level,
+                         dr3lk_pyramid** out);
+void dr3lk_pyramid_destroy(dr3lk_pyramid* pyr);
+int dr3lk_pyramid_levels(const dr3lk_pyramid* pyr); /* effective maxLevel + 1 */
+/* Same semantics and results as dr3lk_calc_optical_flow_pyr_lk on the two source images; win must be the one the
+ * pyramids were built for and max_level is clamped to what they hold. */
+int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const dr3lk_pyramid* next,
+                                          const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n, int win_w,
+                                          int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
+                                          double min_eig_threshold);
+
+/* f-3: the step right after the LK call, reference src/initialization.cpp:615-635 -- drop the points with status == 0
+ * (order preserved, like the erase loop), disparity = ||ref - cur|| (double), and the unit bearing vector of the current
+ * point for an undistorted pinhole camera ((u-cx)/fx, (v-cy)/fy, 1) normalised (src/camera.cpp:25-41, !_distortion).
+ * Host buffers; out_ref/out_cur hold n x 2 floats, out_disparity n doubles, out_bearing n x 3 doubles (may be NULL).
+ * *n_kept receives the number of surviving points. */
+int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_pts, const uint8_t* status, int n, double fx,
+                        double fy, double cx, double cy, float* out_ref, float* out_cur, double* out_disparity,
+                        double* out_bearing, int* n_kept);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,5 +144,75 @@ inline void create_img_pyramid(const Image& img_lvl_0, int n_levels, ImgPyramid&
     c.check(dr3lk_box_pyramid(c.get(), img_lvl_0.data, img_lvl_0.cols, img_lvl_0.rows, img_lvl_0.step, n_levels, outs.data(), mode));
 }
 
+// ---- a frame's LK pyramid built once on the device and reused across calls ----
+class Pyramid {
+public:
+    Pyramid(const Image& img, Size winSize = Size(21, 21), int maxLevel = 3, Context* context = nullptr)
+        : ctx_(context ? context : &Context::thread_default()), pyr_(nullptr), win_(winSize)
+    {
+        ctx_->check(dr3lk_pyramid_create(ctx_->get(), img.data, img.cols, img.rows, img.step, winSize.width, winSize.height, maxLevel, &pyr_));
+    }
+    ~Pyramid() { dr3lk_pyramid_destroy(pyr_); }
+    Pyramid(const Pyramid&) = delete;
+    Pyramid& operator=(const Pyramid&) = delete;
+    const dr3lk_pyramid* get() const { return pyr_; }
+    Context& context() const { return *ctx_; }
+    Size winSize() const { return win_; }
+    int levels() const { return dr3lk_pyramid_levels(pyr_); }
+
+private:
+    Context* ctx_;
+    dr3lk_pyramid* pyr_;
+    Size win_;
+};
+
+// calcOpticalFlowPyrLK on prebuilt pyramids (OpenCV's vector<Mat> pyramid input form); the window is the pyramids'.
+template <class P2f>
+inline void calcOpticalFlowPyrLK(const Pyramid& prevPyr, const Pyramid& nextPyr, const std::vector<P2f>& prevPts, std::vector<P2f>& nextPts,
+                                 std::vector<unsigned char>& status, std::vector<float>& err, int maxLevel = 3,
+                                 TermCriteria criteria = TermCriteria(TermCriteria::COUNT + TermCriteria::EPS, 30, 0.01), int flags = 0,
+                                 double minEigThreshold = 1e-4)
+{
+    static_assert(sizeof(P2f) == 2 * sizeof(float), "points must be two packed floats (x, y)");
+    Context& c = prevPyr.context();
+    const size_t n = prevPts.size();
+    if (n == 0) { nextPts.clear(); status.clear(); err.clear(); return; }
+    if (flags & OPTFLOW_USE_INITIAL_FLOW) {
+        if (nextPts.size() != n) throw Exception(DR3LK_E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints");
+    } else {
+        nextPts.resize(n);
+    }
+    status.resize(n);
+    err.resize(n);
+    const Size win = prevPyr.winSize();
+    c.check(dr3lk_calc_optical_flow_pyr_lk_cached(c.get(), prevPyr.get(), nextPyr.get(), reinterpret_cast<const float*>(prevPts.data()),
+                                                  reinterpret_cast<float*>(nextPts.data()), status.data(), err.data(), static_cast<int>(n),
+                                                  win.width, win.height, maxLevel, criteria.type, criteria.maxCount, criteria.epsilon, flags,
+                                                  minEigThreshold));
+}
+
+// ---- the erase-by-status loop of src/initialization.cpp:615-635 in one call ----
+// Removes the lost points from ref/cur (order kept), fills the disparities and, for an undistorted pinhole, the unit
+// bearing vectors of the current points (3 doubles each; pass fx = 0 to skip them).
+template <class P2f>
+inline void filterTracks(std::vector<P2f>& kpsRef, std::vector<P2f>& kpsCur, const std::vector<unsigned char>& status,
+                         std::vector<double>& disparities, std::vector<double>& bearings, double fx = 0, double fy = 0, double cx = 0,
+                         double cy = 0, Context* context = nullptr)
+{
+    static_assert(sizeof(P2f) == 2 * sizeof(float), "points must be two packed floats (x, y)");
+    Context& c = context ? *context : Context::thread_default();
+    const int n = static_cast<int>(kpsRef.size());
+    std::vector<P2f> r(kpsRef.size()), q(kpsRef.size());
+    disparities.assign(kpsRef.size(), 0.0);
+    bearings.assign(fx != 0 ? 3 * kpsRef.size() : 0, 0.0);
+    int kept = 0;
+    c.check(dr3lk_filter_tracks(c.get(), reinterpret_cast<const float*>(kpsRef.data()), reinterpret_cast<const float*>(kpsCur.data()),
+                                status.data(), n, fx != 0 ? fx : 1.0, fy != 0 ? fy : 1.0, cx, cy, reinterpret_cast<float*>(r.data()),
+                                reinterpret_cast<float*>(q.data()), disparities.data(), fx != 0 ? bearings.data() : nullptr, &kept));
+    r.resize(kept); q.resize(kept); disparities.resize(kept);
+    if (fx != 0) bearings.resize(3 * static_cast<size_t>(kept));
+    kpsRef.swap(r); kpsCur.swap(q);
+}
+
 }  // namespace dr3
 #endif  // DR3LK_HPP_

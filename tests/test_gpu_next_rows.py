@@ -1,0 +1,56 @@
+"""GPU parity of the SURVEY.md 8(f) rows built so far: f-2 pyramid caching and f-3 status filter / disparity / bearings."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import postfilter
+from _common import golden_case, load_gray, random_points
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cached_pyramids_give_identical_results(ctx, dr3):
+    frames = [load_gray("kitti%d.png" % i) for i in range(4)]
+    pts = golden_case("c1_default_21x21")["prev_pts"][:2000]
+    pyrs = [dr3.Pyramid(ctx, f, (21, 21), 3) for f in frames]
+    assert all(p.levels == 4 for p in pyrs)
+    cur = pts
+    for i in range(3):  # frame-to-frame chain: every pyramid is built once and used as next, then as prev
+        got = ctx.calc_optical_flow_pyr_lk_cached(pyrs[i], pyrs[i + 1], cur)
+        exp = ctx.calc_optical_flow_pyr_lk(frames[i], frames[i + 1], cur)
+        orc = oracle.calc_optical_flow_pyr_lk(frames[i], frames[i + 1], cur)
+        for a, b, c in zip(got, exp, orc):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)) and np.array_equal(a.view(np.uint8), c.view(np.uint8))
+        cur = got[0][got[1] == 1]
+    # anchored retries against the same reference frame with warm start (the reference's actual loop)
+    init = pts + np.float32(0.75)
+    got = ctx.calc_optical_flow_pyr_lk_cached(pyrs[0], pyrs[2], pts, init, 3, (3, 30, 0.01), dr3.USE_INITIAL_FLOW)
+    orc = oracle.calc_optical_flow_pyr_lk(frames[0], frames[2], pts, init, (21, 21), 3, (3, 30, 0.01), dr3.USE_INITIAL_FLOW)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc))
+    # fewer levels than the pyramids hold, and mismatched windows / sizes are rejected like OpenCV does
+    got = ctx.calc_optical_flow_pyr_lk_cached(pyrs[0], pyrs[1], pts, max_level=1)
+    orc = oracle.calc_optical_flow_pyr_lk(frames[0], frames[1], pts, None, (21, 21), 1)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc))
+    other = dr3.Pyramid(ctx, frames[0][:, :-8], (21, 21), 3)
+    with pytest.raises(dr3.Dr3lkError):
+        ctx.calc_optical_flow_pyr_lk_cached(pyrs[0], other, pts)
+    for p in pyrs + [other]:
+        p.close()
+
+
+def test_filter_tracks_matches_restatement(ctx):
+    rng = np.random.default_rng(12)
+    for n in (1, 7, 1023, 1024, 1025, 4607, 20000):
+        ref = random_points(rng, 1240, 376, n)
+        cur = (ref + rng.normal(0, 3, ref.shape)).astype(np.float32)
+        st = (rng.random(n) < 0.9).astype(np.uint8)
+        got = ctx.filter_tracks(ref, cur, st, 718.856, 718.856, 607.1928, 185.2157)  # KITTI sequence-00 intrinsics
+        exp = postfilter.filter_tracks(ref, cur, st, 718.856, 718.856, 607.1928, 185.2157)
+        assert len(got[0]) == int(st.sum())
+        for a, b in zip(got, exp):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), n
+        assert np.allclose(np.linalg.norm(got[3], axis=1), 1.0, atol=1e-15)
+    r, c, d, b = ctx.filter_tracks(ref, cur, np.zeros(len(ref), np.uint8))
+    assert len(r) == 0 and len(d) == 0 and b is None
+    r, c, d, b = ctx.filter_tracks(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.uint8))
+    assert len(r) == 0

@@ -61,6 +61,20 @@ def chain(track):
 
 t = time_call(lambda: chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c)), n=10)
 tc = time_call(lambda: chain(lambda x, y, c: cv2_ref.calc_optical_flow_pyr_lk(x, y, c)), n=3, warm=1)
+
+def chain_cached():
+    pyrs = [dr3.Pyramid(ctx, f, (21, 21), 3) for f in frames]
+    cur, surv = pts, []
+    for i in range(9):
+        p, s, _ = ctx.calc_optical_flow_pyr_lk_cached(pyrs[i], pyrs[i + 1], cur)
+        cur = p[s == 1]; surv.append(len(cur))
+    for q in pyrs:
+        q.close()
+    return surv
+
+
+t_cached = time_call(chain_cached, n=10)
+out["c2_chain_cached_pyramids_ms"] = 1e3 * t_cached
 out["c2_chain"] = {"survivors": chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c)), "gpu_chain_ms": 1e3 * t, "cv2_chain_ms": 1e3 * tc}
 
 
