@@ -104,6 +104,17 @@ struct dr3lk_ctx {
     uint64_t launches = 0;
     Workspace ws;                 // single-call / device-batch scratch
     HostBuf pinned;               // staging for the single-pair host call
+    std::vector<DevBuf> pool;     // device buffers of destroyed dr3lk_pyramid objects, reused by the next create
+    DevBuf take(size_t bytes)
+    {
+        for (size_t i = 0; i < pool.size(); i++)
+            if (pool[i].cap >= bytes && pool[i].cap <= bytes + bytes / 4 + 4096) {
+                DevBuf b = pool[i];
+                pool.erase(pool.begin() + i);
+                return b;
+            }
+        return DevBuf();
+    }
     bool profiling = false;
     struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
     std::vector<Prof> prof;
@@ -353,6 +364,7 @@ void dr3lk_destroy(dr3lk_ctx* ctx)
     cudaDeviceSynchronize();
     ctx->ws.release();
     ctx->pinned.release();
+    for (auto& b : ctx->pool) b.release();
     for (int i = 0; i < dr3lk_ctx::kSlots; i++) {
         ctx->slot_ws[i].release();
         if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
@@ -764,6 +776,8 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     const PyrLayout& P = p->P;
     size_t img_total = 0, der_total = 0, ioff[kMaxLevels], doff[kMaxLevels];
     for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
+    p->img = ctx->take(img_total);
+    p->deriv = ctx->take(der_total * sizeof(int));
     cudaError_t e = p->img.reserve(img_total);
     if (e == cudaSuccess) e = p->deriv.reserve(der_total * sizeof(int));
     if (e == cudaSuccess) e = ctx->pinned.reserve(P.img_bytes[0]);
@@ -805,8 +819,9 @@ void dr3lk_pyramid_destroy(dr3lk_pyramid* pyr)
 {
     if (!pyr) return;
     cudaSetDevice(pyr->ctx->device);
-    pyr->img.release();
-    pyr->deriv.release();
+    // stream-ordered reuse is safe: every consumer of these buffers was enqueued on the context's stream before this point
+    if (pyr->ctx->pool.size() < 16) { pyr->ctx->pool.push_back(pyr->img); pyr->ctx->pool.push_back(pyr->deriv); }
+    else { pyr->img.release(); pyr->deriv.release(); }
     delete pyr;
 }
 

@@ -63,13 +63,16 @@ t = time_call(lambda: chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c
 tc = time_call(lambda: chain(lambda x, y, c: cv2_ref.calc_optical_flow_pyr_lk(x, y, c)), n=3, warm=1)
 
 def chain_cached():
-    pyrs = [dr3.Pyramid(ctx, f, (21, 21), 3) for f in frames]
+    # streaming use: one pyramid per incoming frame, the previous frame's pyramid is reused as the LK template side
+    prev_pyr = dr3.Pyramid(ctx, frames[0], (21, 21), 3)
     cur, surv = pts, []
     for i in range(9):
-        p, s, _ = ctx.calc_optical_flow_pyr_lk_cached(pyrs[i], pyrs[i + 1], cur)
+        nxt_pyr = dr3.Pyramid(ctx, frames[i + 1], (21, 21), 3)
+        p, s, _ = ctx.calc_optical_flow_pyr_lk_cached(prev_pyr, nxt_pyr, cur)
         cur = p[s == 1]; surv.append(len(cur))
-    for q in pyrs:
-        q.close()
+        prev_pyr.close()
+        prev_pyr = nxt_pyr
+    prev_pyr.close()
     return surv
 
 
@@ -115,5 +118,13 @@ t, tracked, n = device_batch(np.stack([a5] * 256), np.stack([b5] * 256), [p5] * 
 tc = cpu_time(a5, b5, p5, (21, 21), 3, (3, 30, 0.01), n=3)
 out["c5_semidense"] = {"pairs": 256, "points_per_pair": len(p5), "tracked_fraction": tracked / n, "gpu_features_per_s": n / t,
                        "cv2_features_per_s": len(p5) / tc}
+# ---- KITTI batch: the 9 bundled consecutive pairs kitti0..9 tiled to 2304 device-resident pairs, FAST corners of each prev frame
+kp = [cv2_ref.fast_corners(frames[i])[0] for i in range(9)]
+reps = 256
+prev_k = np.stack([frames[i] for i in range(9)] * reps); next_k = np.stack([frames[i + 1] for i in range(9)] * reps)
+t, tracked, n = device_batch(prev_k, next_k, kp * reps, (21, 21), 3, (3, 30, 0.01))
+tc = sum(cpu_time(frames[i], frames[i + 1], kp[i], (21, 21), 3, (3, 30, 0.01), n=3) for i in range(9))
+out["kitti_batch_21x21"] = {"pairs": 9 * reps, "points": n, "tracked_fraction": tracked / n, "gpu_features_per_s": n / t,
+                            "gpu_tracked_per_s": tracked / t, "cv2_features_per_s": sum(len(k) for k in kp) / tc}
 out["host"] = {"cpus": os.cpu_count(), "cv2": cv2_ref.CV2_VERSION, "gpu": torch.cuda.get_device_name(0)}
 print(json.dumps(out, indent=1))
