@@ -32,7 +32,7 @@ SYMBOLS = [
     "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
-    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks",
+    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks", "dr3lk_fast_detect",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
     L.dr3lk_calc_optical_flow_pyr_lk_cached.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
     L.dr3lk_filter_tracks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, P(c_int)]
+    L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, P(c_int)]
     _lib = L
     return L
 
@@ -285,6 +287,21 @@ class Context:
                                               bear.ctypes.data if bear is not None else None, ctypes.byref(k)))
         k = k.value
         return o_r[:k], o_c[:k], disp[:k], (bear[:k] if bear is not None else None)
+
+    def fast_detect(self, img, n_levels=3, cell_size=30, fast_threshold=20, detection_threshold=20.0, occupancy=None,
+                    box_mode=BOX_AUTO_X86):
+        """FastDetector::detect of the reference (src/features.cpp:43-98): returns (xy (n,2) int32 level-0 pixels,
+        level (n,) int32, score (n,) float32) in grid-cell order."""
+        img0 = np.ascontiguousarray(_gray(img))
+        h, w = img0.shape
+        ncell = (-(-w // cell_size)) * (-(-h // cell_size))
+        xy, lv, sc = np.zeros((ncell, 2), np.int32), np.zeros(ncell, np.int32), np.zeros(ncell, np.float32)
+        occ = np.ascontiguousarray(occupancy, np.uint8) if occupancy is not None else None
+        n = ctypes.c_int(0)
+        self._check(lib().dr3lk_fast_detect(self._h, img0.ctypes.data, w, h, img0.strides[0], n_levels, cell_size, fast_threshold,
+                                            float(detection_threshold), box_mode, occ.ctypes.data if occ is not None else None,
+                                            xy.ctypes.data, lv.ctypes.data, sc.ctypes.data, ctypes.byref(n)))
+        return xy[:n.value].copy(), lv[:n.value].copy(), sc[:n.value].copy()
 
     def track_batch(self, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,
                     err_ptr, pts_offset, stats_ptr=None, win=(21, 21), max_level=3,

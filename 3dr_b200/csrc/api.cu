@@ -925,4 +925,84 @@ int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_p
     return DR3LK_OK;
 }
 
+
+/* ---------------------------------------------------------------------------------------------- */
+/* f-1: FAST-10 + grid Shi-Tomasi selection                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+
+int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size, int fast_threshold,
+                      double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score,
+                      int* n_out)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (!img || !out_xy || !out_level || !out_score || !n_out || step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "fast_detect: bad argument");
+    if (n_levels < 1 || n_levels > 8 || cell_size < 1 || fast_threshold < 0 || fast_threshold > 254)
+        return fail(ctx, DR3LK_E_ARG, "fast_detect: n_levels must be 1..8, cell_size >= 1, threshold 0..254");
+    if (box_mode < DR3LK_BOX_AUTO_X86 || box_mode > DR3LK_BOX_SSE2) return fail(ctx, DR3LK_E_ARG, "fast_detect: bad box mode");
+    if (w < 7 || h < 7 || (long long)w * h >= (1ll << 28)) return fail(ctx, DR3LK_E_SIZE, "fast_detect: image must be 7x7 .. 2^28 pixels");
+    *n_out = 0;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    // box pyramid shapes (validated like dr3lk_box_pyramid) and the packed device layout
+    int lw[8], lh[8], sse2[8] = {0};
+    size_t off[8], total = 0;
+    {
+        long long row = (long long)step;
+        bool aligned = (reinterpret_cast<uintptr_t>(img) & 0xF) == 0;
+        lw[0] = w; lh[0] = h;
+        for (int l = 0; l < n_levels; l++) {
+            off[l] = total;
+            total += align_up_sz((size_t)lw[l] * lh[l], 256);
+            if (l + 1 < n_levels) {
+                int rc = box_level_mode(ctx, lw[l], lh[l], l == 0 ? row : (long long)lw[l], box_mode, l == 0 ? aligned : true, &sse2[l + 1]);
+                if (rc != DR3LK_OK) return rc;
+                lw[l + 1] = lw[l] / 2; lh[l + 1] = lh[l] / 2;
+            }
+        }
+    }
+    const int gc = (w + cell_size - 1) / cell_size, gr = (h + cell_size - 1) / cell_size, ncell = gc * gr;
+    // device block: [levels][score maps][cell keys 8*ncell][occupancy ncell][level widths 32][out xy 8n][level 4n][score 4n][count 16]
+    const size_t o_score = total, o_keys = align_up_sz(2 * total, 256), o_occ = o_keys + align_up_sz(8 * (size_t)ncell, 16),
+                 o_lw = o_occ + align_up_sz((size_t)ncell, 16), o_xy = o_lw + 32, o_lv = o_xy + align_up_sz(8 * (size_t)ncell, 16),
+                 o_sc = o_lv + align_up_sz(4 * (size_t)ncell, 16), o_cnt = o_sc + align_up_sz(4 * (size_t)ncell, 16), dev_total = o_cnt + 16;
+    CU_TRY(ctx, W.lvl0_next.reserve(dev_total));
+    uint8_t* dp = (uint8_t*)W.lvl0_next.p;
+    // pinned mirror: level 0 rows packed to w bytes, occupancy, level widths; outputs come back into the same mirror
+    const size_t h_img = align_up_sz((size_t)w * h, 16), h_total = h_img + align_up_sz((size_t)ncell, 16) + 32 + (dev_total - o_xy);
+    CU_TRY(ctx, ctx->pinned.reserve(h_total));
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    // the Frame's image is a continuous cv::Mat; the box-pyramid walk of a strided ROI is garbage in the reference itself
+    if (step != (size_t)w) return fail(ctx, DR3LK_E_UNSUPPORTED, "fast_detect: continuous images only (step == width)");
+    memcpy(hp, img, (size_t)w * h);
+    uint8_t* h_occ = hp + h_img;
+    if (occupancy) memcpy(h_occ, occupancy, (size_t)ncell);
+    int* h_lw = (int*)(h_occ + align_up_sz((size_t)ncell, 16));
+    for (int l = 0; l < 8; l++) h_lw[l] = l < n_levels ? lw[l] : 1;
+    CU_TRY(ctx, cudaMemcpyAsync(dp + off[0], hp, (size_t)w * h, cudaMemcpyHostToDevice, st));
+    if (occupancy) CU_TRY(ctx, cudaMemcpyAsync(dp + o_occ, h_occ, (size_t)ncell, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(dp + o_lw, h_lw, 32, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(dp + o_keys, 0, 8 * (size_t)ncell, st));
+    Launch L{st, cudaSuccess, 0};
+    for (int l = 1; l < n_levels; l++)
+        launch_box_half(L, dp + off[l - 1], lw[l - 1], lh[l - 1], lw[l - 1], 0, dp + off[l], 0, 1, sse2[l]);
+    for (int l = 0; l < n_levels; l++)
+        if (lw[l] >= 7 && lh[l] >= 7)
+            launch_fast_level(L, dp + off[l], dp + o_score + off[l], lw[l], lh[l], l, fast_threshold, cell_size, gc, (float)detection_threshold,
+                              detection_threshold, occupancy ? dp + o_occ : nullptr, (unsigned long long*)(dp + o_keys));
+    launch_fast_gather(L, (const unsigned long long*)(dp + o_keys), ncell, (const int*)(dp + o_lw), (int*)(dp + o_xy), (int*)(dp + o_lv),
+                       (float*)(dp + o_sc), (int*)(dp + o_cnt));
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "fast_detect kernel launch");
+    uint8_t* h_out = (uint8_t*)h_lw + 32;
+    CU_TRY(ctx, cudaMemcpyAsync(h_out, dp + o_xy, dev_total - o_xy, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    const int n = *reinterpret_cast<const int*>(h_out + (o_cnt - o_xy));
+    *n_out = n;
+    memcpy(out_xy, h_out, 8 * (size_t)n);
+    memcpy(out_level, h_out + (o_lv - o_xy), 4 * (size_t)n);
+    memcpy(out_score, h_out + (o_sc - o_xy), 4 * (size_t)n);
+    return DR3LK_OK;
+}
+
 }  // extern "C"

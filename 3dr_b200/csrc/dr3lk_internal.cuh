@@ -70,6 +70,12 @@ void launch_pyr_level(Launch& L, const PyrLevelArgs& a);
 void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
                      uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding);
 
+// fast.cu
+void launch_fast_level(Launch& L, const uint8_t* img, uint8_t* score, int w, int h, int level, int fast_threshold, int cell_size,
+                       int grid_cols, float thr_f, double thr_d, const uint8_t* occupancy, unsigned long long* cell_best);
+void launch_fast_gather(Launch& L, const unsigned long long* cell_best, int n_cells, const int* level_w, int* out_xy, int* out_level,
+                        float* out_score, int* n_out);
+
 // filter.cu
 void launch_filter_tracks(Launch& L, const float* ref, const float* cur, const uint8_t* status, int n, double fx, double fy, double cx,
                           double cy, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept);

@@ -147,6 +147,18 @@ int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_p
                         double fy, double cx, double cy, float* out_ref, float* out_cur, double* out_disparity,
                         double* out_bearing, int* n_kept);
 
+/* f-1 / a-10: the prevPts provider -- feature_detection::FastDetector::detect (reference src/features.cpp:43-98) on
+ * the Frame's box pyramid (utils::create_img_pyramid, n_levels levels, rounding `box_mode`): FAST-10 corners
+ * (threshold fast_threshold, 20 in the reference), fast_corner_score_10, fast_nonmax_3x3, then per grid cell of
+ * cell_size pixels the corner with the best utils::shi_tomasi_score above detection_threshold
+ * (Config::cell_size() = 30, Config::min_harris_corner_score() = 20.0, src/config.cpp:9-12).
+ * occupancy: ceil(w/cell) * ceil(h/cell) bytes, non-zero = cell already taken (NULL = all free).
+ * Outputs, in grid-cell order like the reference's feature list: out_xy level-0 pixel coordinates (2 ints each),
+ * out_level, out_score; capacity ceil(w/cell)*ceil(h/cell) entries each.  Host buffers, synchronous. */
+int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size,
+                      int fast_threshold, double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy,
+                      int* out_level, float* out_score, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

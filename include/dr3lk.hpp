@@ -214,5 +214,28 @@ inline void filterTracks(std::vector<P2f>& kpsRef, std::vector<P2f>& kpsCur, con
     kpsRef.swap(r); kpsCur.swap(q);
 }
 
+// ---- feature_detection::FastDetector::detect (src/features.cpp:43-98) ----
+struct Corner {  // reference include/features.hpp:66-77
+    int x, y, level;
+    float score;
+};
+// FAST-10 corners of the frame's box pyramid, one per grid cell (best Shi-Tomasi score above detection_threshold), in
+// cell order.  Defaults are the reference's Config values (src/config.cpp:9-12) and FAST threshold (features.cpp:57).
+inline std::vector<Corner> fastDetect(const Image& img, int n_pyr_levels = 3, int cell_size = 30, double detection_threshold = 20.0,
+                                      int fast_threshold = 20, const std::vector<unsigned char>* grid_occupancy = nullptr,
+                                      int box_mode = DR3LK_BOX_AUTO_X86, Context* context = nullptr)
+{
+    Context& c = context ? *context : Context::thread_default();
+    const size_t cells = static_cast<size_t>((img.cols + cell_size - 1) / cell_size) * static_cast<size_t>((img.rows + cell_size - 1) / cell_size);
+    std::vector<int> xy(2 * cells), lv(cells);
+    std::vector<float> sc(cells);
+    int n = 0;
+    c.check(dr3lk_fast_detect(c.get(), img.data, img.cols, img.rows, img.step, n_pyr_levels, cell_size, fast_threshold, detection_threshold,
+                              box_mode, grid_occupancy ? grid_occupancy->data() : nullptr, xy.data(), lv.data(), sc.data(), &n));
+    std::vector<Corner> out(static_cast<size_t>(n));
+    for (int i = 0; i < n; i++) out[i] = Corner{xy[2 * i], xy[2 * i + 1], lv[i], sc[i]};
+    return out;
+}
+
 }  // namespace dr3
 #endif  // DR3LK_HPP_

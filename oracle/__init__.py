@@ -22,8 +22,8 @@ _lib = None
 
 def build(force=False):
     """Compile oracle/lk_oracle.c with gcc (oracle/Makefile)."""
-    src = os.path.join(_HERE, "lk_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("lk_oracle.c", "fast_oracle.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -43,6 +43,13 @@ def lib():
                                                    c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_double, c_int,
                                                    i32p, u8p, f32p]
         L.orc_num_threads.restype = c_int
+        i16p2 = ctypes.POINTER(ctypes.c_int16)
+        L.orc_fast_detect.argtypes = [u8p, c_int, c_int, c_long, c_int, c_int, i16p2, c_int]
+        L.orc_fast_score.argtypes = [u8p, c_long, i16p2, c_int, c_int, c_int, i32p]
+        L.orc_fast_nonmax.argtypes = [i16p2, i32p, c_int, i32p]
+        L.orc_shi_tomasi.argtypes = [u8p, c_int, c_int, c_long, c_int, c_int]
+        L.orc_shi_tomasi.restype = ctypes.c_float
+        L.orc_fast_detector.argtypes = [ctypes.POINTER(u8p), c_int, c_int, c_int, c_int, c_int, c_double, u8p, i32p, i32p, f32p]
         _lib = L
     return _lib
 
@@ -148,6 +155,54 @@ def calc_optical_flow_pyr_lk(prev, nxt, prev_pts, next_pts=None, win=(21, 21), m
     if trace:
         return npts, status, err, {"iters": ti, "code": tc, "pos": tp, "max_level": rc}
     return npts, status, err
+
+
+def fast_detect(img, threshold=20, arc=10):
+    """fast_corner_detect_<arc>: (n, 2) int16 corners (x, y) in raster order."""
+    img = np.ascontiguousarray(_gray(img))
+    h, w = img.shape
+    xy = np.zeros((w * h, 2), np.int16)
+    n = lib().orc_fast_detect(_p(img, ctypes.c_uint8), w, h, w, threshold, arc, _p(xy, ctypes.c_int16), w * h)
+    return xy[:n].copy()
+
+
+def fast_score(img, xy, threshold=20, arc=10):
+    img = np.ascontiguousarray(_gray(img))
+    xy = np.ascontiguousarray(xy, np.int16)
+    sc = np.zeros(len(xy), np.int32)
+    lib().orc_fast_score(_p(img, ctypes.c_uint8), img.shape[1], _p(xy, ctypes.c_int16), len(xy), threshold, arc, _p(sc, ctypes.c_int32))
+    return sc
+
+
+def fast_nonmax(xy, scores):
+    xy = np.ascontiguousarray(xy, np.int16)
+    scores = np.ascontiguousarray(scores, np.int32)
+    keep = np.zeros(max(len(xy), 1), np.int32)
+    n = lib().orc_fast_nonmax(_p(xy, ctypes.c_int16), _p(scores, ctypes.c_int32), len(xy), _p(keep, ctypes.c_int32))
+    return keep[:n].copy()
+
+
+def shi_tomasi(img, u, v):
+    img = np.ascontiguousarray(_gray(img))
+    return float(lib().orc_shi_tomasi(_p(img, ctypes.c_uint8), img.shape[1], img.shape[0], img.shape[1], int(u), int(v)))
+
+
+def fast_detector(img, n_levels=3, cell_size=30, fast_threshold=20, detection_threshold=20.0, occupancy=None, box_mode=BOX_AUTO_X86):
+    """FastDetector::detect on the Frame's box pyramid (src/features.cpp:43-98, src/frame.cpp:13-20).
+    Returns (xy (n,2) int32 level-0 coordinates, level (n,), score (n,) float32) in grid-cell order."""
+    pyr = [np.ascontiguousarray(p) for p in box_pyramid(img, n_levels, box_mode)]
+    h, w = pyr[0].shape
+    gc, gr = -(-w // cell_size), -(-h // cell_size)
+    ptrs = (ctypes.POINTER(ctypes.c_uint8) * n_levels)(*[_p(p, ctypes.c_uint8) for p in pyr])
+    xy = np.zeros((gc * gr, 2), np.int32)
+    lv = np.zeros(gc * gr, np.int32)
+    sc = np.zeros(gc * gr, np.float32)
+    occ = np.ascontiguousarray(occupancy, np.uint8) if occupancy is not None else None
+    n = lib().orc_fast_detector(ptrs, w, h, n_levels, cell_size, fast_threshold, float(detection_threshold),
+                                _p(occ, ctypes.c_uint8) if occ is not None else None, _p(xy, ctypes.c_int32), _p(lv, ctypes.c_int32),
+                                _p(sc, ctypes.c_float))
+    assert n >= 0
+    return xy[:n].copy(), lv[:n].copy(), sc[:n].copy()
 
 
 def num_threads():

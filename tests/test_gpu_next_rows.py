@@ -54,3 +54,42 @@ def test_filter_tracks_matches_restatement(ctx):
     assert len(r) == 0 and len(d) == 0 and b is None
     r, c, d, b = ctx.filter_tracks(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.uint8))
     assert len(r) == 0
+
+
+@pytest.mark.parametrize("name", ["kitti0.png", "kitti5.png", "kitti_000000.png", "sample_gray_500x375.png"])
+def test_fast_detector_matches_restatement(ctx, name):
+    """f-1: FAST-10 + score + 3x3 non-max + per-cell Shi-Tomasi selection on the Frame's box pyramid."""
+    im = load_gray(name)
+    got = ctx.fast_detect(im, 3, 30, 20, 20.0)
+    exp = oracle.fast_detector(im, 3, 30, 20, 20.0)
+    assert len(got[0]) == len(exp[0]) > 100
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+    assert np.array_equal(got[2].view(np.uint32), exp[2].view(np.uint32))
+
+
+def test_fast_detector_parameters_and_occupancy(ctx, dr3):
+    from tools import synth
+    rng = np.random.default_rng(21)
+    a, _, _ = synth.make_pair(3001, 1280, 720)  # 1280 % 16 == 0: the box pyramid takes the SSE2 rounding on x86
+    for (nl, cell, thr, det, mode) in [(3, 30, 20, 20.0, 0), (1, 16, 10, 5.0, 0), (4, 40, 35, 50.0, 1), (2, 25, 20, 0.0, 2)]:
+        got = ctx.fast_detect(a, nl, cell, thr, det, None, mode)
+        exp = oracle.fast_detector(a, nl, cell, thr, det, None, mode)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2]), (nl, cell, thr)
+    ncell = (-(-1280 // 30)) * (-(-720 // 30))
+    occ = (rng.random(ncell) < 0.5).astype(np.uint8)
+    got = ctx.fast_detect(a, 3, 30, 20, 20.0, occ)
+    exp = oracle.fast_detector(a, 3, 30, 20, 20.0, occ)
+    assert len(got[0]) > 50 and np.array_equal(got[0], exp[0]) and np.array_equal(got[2], exp[2])
+    cells = (got[0][:, 1] // 30) * (-(-1280 // 30)) + got[0][:, 0] // 30
+    assert not occ[cells].any()
+    flat = np.full((100, 120), 9, np.uint8)
+    assert len(ctx.fast_detect(flat)[0]) == 0
+    with pytest.raises(dr3.Dr3lkError):
+        ctx.fast_detect(np.zeros((375, 501), np.uint8))  # odd x odd level: the reference overruns its pyramid buffers
+    # the detector's corners feed the LK call, as in Init::process_first_frame -> process_second_frame
+    b = load_gray("kitti1.png")
+    k0 = load_gray("kitti0.png")
+    xy, lv, sc = ctx.fast_detect(k0)
+    p, s, e = ctx.calc_optical_flow_pyr_lk(k0, b, xy.astype(np.float32), xy.astype(np.float32), (30, 30), 4, (3, 1000, 1e-3), dr3.USE_INITIAL_FLOW)
+    po, so, eo = oracle.calc_optical_flow_pyr_lk(k0, b, xy.astype(np.float32), xy.astype(np.float32), (30, 30), 4, (3, 1000, 1e-3), 4)
+    assert s.sum() >= 100 and np.array_equal(s, so) and np.array_equal(p.view(np.uint32), po.view(np.uint32))

@@ -1,0 +1,53 @@
+"""CPU tests of the FAST-10 / grid-selection restatement (oracle/fast_oracle.c).
+Parity for this row is unpinned (the `fast` library is absent); what can be pinned is checked here: the corner test
+against cv2's FAST-9 by running the same code with arc length 9, and internal consistency of score / non-max / grid."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import cv2_ref
+from _common import load_gray
+
+
+@pytest.mark.skipif(not cv2_ref.HAVE_CV2, reason="cv2 not importable")
+@pytest.mark.parametrize("name", ["kitti0.png", "kitti_000000.png", "sample_gray_500x375.png"])
+def test_corner_test_matches_cv2_fast9(name):
+    im = load_gray(name)
+    det = cv2_ref.cv2.FastFeatureDetector_create(20, False, cv2_ref.cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    cvp = sorted((int(k.pt[1]), int(k.pt[0])) for k in det.detect(im, None))
+    mine = sorted((int(y), int(x)) for x, y in oracle.fast_detect(im, 20, 9))
+    assert mine == cvp and len(mine) > 1000
+
+
+def test_score_is_largest_threshold_and_nonmax_is_8_neighbour():
+    im = load_gray("kitti1.png")
+    xy = oracle.fast_detect(im, 20, 10)
+    sc = oracle.fast_score(im, xy, 20, 10)
+    assert len(xy) > 5000 and sc.min() >= 20 and sc.max() <= 254
+    # raising the threshold to score keeps the corner, score + 1 drops it
+    for i in np.random.default_rng(0).choice(len(xy), 40, replace=False):
+        x, y, s = int(xy[i, 0]), int(xy[i, 1]), int(sc[i])
+        patch = np.ascontiguousarray(im[y - 3:y + 4, x - 3:x + 4])
+        assert len(oracle.fast_detect(patch, s, 10)) == 1 and len(oracle.fast_detect(patch, s + 1, 10)) == 0
+    keep = oracle.fast_nonmax(xy, sc)
+    smap = np.zeros(im.shape, np.int32)
+    smap[xy[:, 1], xy[:, 0]] = sc
+    pad = np.pad(smap, 1)
+    nb = np.max([pad[1 + dy:1 + dy + im.shape[0], 1 + dx:1 + dx + im.shape[1]] for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dy, dx) != (0, 0)], axis=0)
+    exp = [i for i in range(len(xy)) if nb[xy[i, 1], xy[i, 0]] < sc[i]]
+    assert list(keep) == exp
+
+
+def test_detector_grid_properties():
+    im = load_gray("kitti0.png")
+    xy, lv, sc = oracle.fast_detector(im, 3, 30, 20, 20.0)
+    assert 200 < len(xy) <= 42 * 13 and (sc > 20.0).all() and set(np.unique(lv)) <= {0, 1, 2}
+    cells = (xy[:, 1] // 30) * 42 + xy[:, 0] // 30
+    assert (np.diff(cells) > 0).all()                         # one feature per cell, in cell order
+    assert ((xy % (1 << lv)[:, None]) == 0).all()             # level-l corners sit on the 2^l lattice
+    # occupied cells are skipped
+    occ = np.zeros(42 * 13, np.uint8)
+    occ[cells[::2]] = 1
+    xy2, _, _ = oracle.fast_detector(im, 3, 30, 20, 20.0, occupancy=occ)
+    cells2 = (xy2[:, 1] // 30) * 42 + xy2[:, 0] // 30
+    assert set(cells2) == set(cells[1::2])
