@@ -276,8 +276,17 @@ def main():
     hbm_peak, peak_src = peaks()
     lk_ms_avg = lk_ms / max(lk_n, 1)
     achieved = alg_bytes / (lk_ms_avg * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "lk_track (LK kernel alone, all levels in one launch)", "achieved": achieved, "peak": hbm_peak,
-            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+    # DRAM traffic of the LK launch: bytes/feature from the committed ncu --set full capture, scaled to this launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "lk_traffic_r01.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_feature"] * n_feat
+        traffic_src = "dram__bytes_read+write.sum per feature from %s, x %d features" % (tj["source"], n_feat)
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "lk_fast_kernel (LK kernel alone, all levels in one launch)", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "lk_ms_per_launch": lk_ms_avg, "pyramid_ms_per_step": pyr_ms / max(lk_n, 1),
             "lk_iterations_per_feature": iters_per_feat,
             "note": "algorithmic bytes = sum over features of (5T*levels_with_template + T*iterations + T*err_pass + 21), T=(21+1)^2 "
