@@ -10,10 +10,11 @@
 //   * The window is cut into runs of R consecutive pixels of one row; each lane owns NRUN runs.  A run's R+1 source
 //     bytes of two rows are fetched as 3-4 aligned 32-bit shared loads and realigned with PRMT, and the 14-bit
 //     bilinear blend is two IDP.2A (dp2a: 2 x (s16 weight * u8 pixel)) per pixel instead of four IMADs.
-//   * The template (Ix, Iy per pixel) lives in registers for the whole level.  sum((J - I) * Ix) is evaluated as
-//     sum(J * Ix) - sum(I * Ix): the second term is constant per level, so an iteration costs 2 IDP + 1 shift +
-//     2 IMAD per pixel.  All sums are exact integers: per-lane int32 partials, warp totals through REDUX on the
-//     16-bit halves, one rounding to fp32 -- results do not depend on summation order.
+//   * The template (Ix, Iy per pixel) lives in registers for the whole level, and so does 2^8 - 512 * I per pixel: used
+//     as the dp2a addend it makes the shifted blend come out as (J - I) directly (a multiple of 512 passes through the
+//     arithmetic >> 9 exactly), so an iteration costs 2 IDP + 1 shift + 2 IMAD per pixel.  All sums are exact
+//     integers: per-lane int32 partials, warp totals through REDUX on the 16-bit halves, one rounding to fp32 --
+//     results do not depend on summation order.
 //   * Scalar fp32 steps use explicitly rounded intrinsics (no FMA contraction) and match the CPU oracle bit for bit.
 #include <float.h>
 
@@ -135,14 +136,15 @@ struct RunBytes {
             bO[j] = __byte_perm(b[j], b[j + 1 < NWD ? j + 1 : j], selO);
         }
     }
-    // (S + 2^8) >> 9 for pixel k of the run
-    __device__ __forceinline__ int sample(int k, const Weights& q) const
+    // (S + init) >> 9 for pixel k of the run.  init = 2^8 gives the window value with 5 fractional bits; init =
+    // 2^8 - 512 * I gives (J - I) directly: subtracting a multiple of 512 before the arithmetic shift is exact.
+    __device__ __forceinline__ int sample(int k, const Weights& q, int init = 1 << (W_BITS - 5 - 1)) const
     {
         const unsigned tt = (k & 1) ? tO[k >> 2] : tE[k >> 2];
         const unsigned bb = (k & 1) ? bO[k >> 2] : bE[k >> 2];
         int s;
-        if (k & 2) { s = dp2a_hi(q.wt, tt, 1 << (W_BITS - 5 - 1)); s = dp2a_hi(q.wb, bb, s); }
-        else { s = dp2a_lo(q.wt, tt, 1 << (W_BITS - 5 - 1)); s = dp2a_lo(q.wb, bb, s); }
+        if (k & 2) { s = dp2a_hi(q.wt, tt, init); s = dp2a_hi(q.wb, bb, s); }
+        else { s = dp2a_lo(q.wt, tt, init); s = dp2a_lo(q.wb, bb, s); }
         return s >> (W_BITS - 5);
     }
 };
@@ -394,8 +396,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             __syncwarp();
 
             int dxr[NRUN][R], dyr[NRUN][R];
-            unsigned i5p[NRUN][(R + 1) / 2];
-            int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
+            int jinit[NRUN][R];  // 2^8 - 512 * I: the dp2a addend that turns the J sample into (J - I)
+            int a11 = 0, a12 = 0, a22 = 0;
             Weights q;
             if (inb) {
                 // ---- template: (I, Ix, Iy) of the window into registers, Gram matrix ----
@@ -422,9 +424,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                         int iy = (ty[k] * q.w00 + ty[k + 1] * q.w01 + by[k] * q.w10 + by[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
                         if (G::RAGGED && k >= WW - (G::NCB - 1) * R && rlast[s]) { ix = 0; iy = 0; }  // pixels past the window edge
                         dxr[s][k] = ix; dyr[s][k] = iy;
-                        if (k & 1) i5p[s][k >> 1] |= (unsigned)i5 << 16; else i5p[s][k >> 1] = (unsigned)i5;
+                        jinit[s][k] = (1 << (W_BITS - 5 - 1)) - (i5 << (W_BITS - 5));
                         a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                        c1 += i5 * ix; c2 += i5 * iy;
                     }
                 }
             }
@@ -440,10 +441,6 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 continue;
             }
             const HiLo s11 = warp_sum_hilo(a11), s12 = warp_sum_hilo(a12), s22 = warp_sum_hilo(a22);
-            const HiLo sc1 = warp_sum_hilo(c1), sc2 = warp_sum_hilo(c2);
-            // normalise the constants sum(I*Ix), sum(I*Iy) to hi * 65536 + lo with 0 <= lo < 65536
-            const int c1hi = sc1.hi + (sc1.lo >> 16), c1lo = sc1.lo & 0xffff;
-            const int c2hi = sc2.hi + (sc2.lo >> 16), c2lo = sc2.lo & 0xffff;
 
             const float A11 = __fmul_rn(hilo_to_float(s11.hi, s11.lo), FLT_SCALE);
             const float A12 = __fmul_rn(hilo_to_float(s12.hi, s12.lo), FLT_SCALE);
@@ -487,16 +484,16 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     rb.load(sJ, jbase + jofs[s]);
 #pragma unroll
                     for (int k = 0; k < R; k++) {
-                        const int j5 = rb.sample(k, q);
-                        b1 += j5 * dxr[s][k];
-                        b2 += j5 * dyr[s][k];
+                        const int diff = rb.sample(k, q, jinit[s][k]);  // J - I
+                        b1 += diff * dxr[s][k];
+                        b2 += diff * dyr[s][k];
                     }
                 }
                 const HiLo sb1 = warp_sum_hilo(b1), sb2 = warp_sum_hilo(b2);
                 n_iters++;
-                // sum((J - I) * Ix) = sum(J * Ix) - sum(I * Ix), exact; one rounding to fp32
-                const float fb1 = __fmul_rn(hilo_to_float(sb1.hi - c1hi, sb1.lo - c1lo), FLT_SCALE);
-                const float fb2 = __fmul_rn(hilo_to_float(sb2.hi - c2hi, sb2.lo - c2lo), FLT_SCALE);
+                // exact integer sums, one rounding to fp32
+                const float fb1 = __fmul_rn(hilo_to_float(sb1.hi, sb1.lo), FLT_SCALE);
+                const float fb2 = __fmul_rn(hilo_to_float(sb2.hi, sb2.lo), FLT_SCALE);
                 const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
                 const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
                 nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
@@ -542,8 +539,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     int e = 0;
 #pragma unroll
                     for (int k = 0; k < R; k++) {
-                        const int i5 = (k & 1) ? (int)(i5p[s][k >> 1] >> 16) : (int)(i5p[s][k >> 1] & 0xffffu);
-                        const int d = abs(rb.sample(k, q) - i5);
+                        const int d = abs(rb.sample(k, q, jinit[s][k]));
                         if (G::RAGGED && k >= WW - (G::NCB - 1) * R) e += rlast[s] ? 0 : d; else e += d;
                     }
                     es += rvalid[s] ? e : 0;
