@@ -32,7 +32,7 @@ SYMBOLS = [
     "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
-    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks", "dr3lk_fast_detect",
+    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
                                       c_void_p, c_void_p, c_void_p, P(c_int)]
     L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, P(c_int)]
+    L.dr3lk_score_fundamental.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p, P(c_int)]
     _lib = L
     return L
 
@@ -302,6 +303,21 @@ class Context:
                                             float(detection_threshold), box_mode, occ.ctypes.data if occ is not None else None,
                                             xy.ctypes.data, lv.ctypes.data, sc.ctypes.data, ctypes.byref(n)))
         return xy[:n.value].copy(), lv[:n.value].copy(), sc[:n.value].copy()
+
+    def score_fundamental(self, F21, pts1, pts2, sigma=1.0, want_inliers=True):
+        """InitHelper::CheckFundamental (src/initialization.cpp:171-249) for a batch of hypotheses.
+        F21 (H,3,3) f32, pts (N,2) f32 -> (scores (H,) f32, inliers (H,N) u8 | None, best index)."""
+        F = np.ascontiguousarray(np.asarray(F21, np.float32).reshape(-1, 9))
+        a = np.ascontiguousarray(np.asarray(pts1, np.float32).reshape(-1, 2))
+        b = np.ascontiguousarray(np.asarray(pts2, np.float32).reshape(-1, 2))
+        assert a.shape == b.shape
+        H, n = F.shape[0], a.shape[0]
+        sc = np.zeros(H, np.float32)
+        inl = np.zeros((H, n), np.uint8) if want_inliers else None
+        best = ctypes.c_int(-1)
+        self._check(lib().dr3lk_score_fundamental(self._h, F.ctypes.data, H, a.ctypes.data, b.ctypes.data, n, float(sigma), sc.ctypes.data,
+                                                  inl.ctypes.data if want_inliers else None, ctypes.byref(best)))
+        return sc, inl, best.value
 
     def track_batch(self, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,
                     err_ptr, pts_offset, stats_ptr=None, win=(21, 21), max_level=3,

@@ -1005,4 +1005,48 @@ int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t s
     return DR3LK_OK;
 }
 
+
+/* ---------------------------------------------------------------------------------------------- */
+/* f-4: RANSAC fundamental-matrix hypothesis scoring                                               */
+/* ---------------------------------------------------------------------------------------------- */
+
+int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, int n, float sigma,
+                            float* out_scores, uint8_t* out_inliers, int* best)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (n_hyp < 0 || n < 0 || !best) return fail(ctx, DR3LK_E_ARG, "score_fundamental: bad argument");
+    *best = -1;
+    if (n_hyp == 0) return DR3LK_OK;
+    if (!F21 || !out_scores || (n > 0 && (!pts1 || !pts2)) || !(sigma > 0.f)) return fail(ctx, DR3LK_E_ARG, "score_fundamental: bad argument");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    const size_t bF = align_up_sz(36 * (size_t)n_hyp, 16), bP = align_up_sz(8 * (size_t)n, 16), bS = align_up_sz(4 * (size_t)n_hyp, 16),
+                 bI = out_inliers ? align_up_sz((size_t)n_hyp * n, 16) : 0;
+    const size_t i_F = 0, i_p1 = bF, i_p2 = bF + bP, o_s = bF + 2 * bP, o_i = o_s + bS, total = o_i + bI;
+    CU_TRY(ctx, W.pts.reserve(total));
+    CU_TRY(ctx, ctx->pinned.reserve(total));
+    uint8_t* dp = (uint8_t*)W.pts.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    memcpy(hp + i_F, F21, 36 * (size_t)n_hyp);
+    if (n > 0) { memcpy(hp + i_p1, pts1, 8 * (size_t)n); memcpy(hp + i_p2, pts2, 8 * (size_t)n); }
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, o_s, cudaMemcpyHostToDevice, st));
+    Launch L{st, cudaSuccess, 0};
+    // const float invSigmaSquare = 1.0/(sigma*sigma): float product, double division, rounded to float
+    const float inv_sigma2 = (float)(1.0 / (double)(sigma * sigma));
+    launch_score_fundamental(L, (const float*)(dp + i_F), n_hyp, (const float*)(dp + i_p1), (const float*)(dp + i_p2), n, inv_sigma2,
+                             (float*)(dp + o_s), out_inliers ? dp + o_i : nullptr);
+    ctx->launches += L.launches;
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "score_fundamental kernel launch");
+    CU_TRY(ctx, cudaMemcpyAsync(hp + o_s, dp + o_s, total - o_s, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    memcpy(out_scores, hp + o_s, 4 * (size_t)n_hyp);
+    if (out_inliers) memcpy(out_inliers, hp + o_i, (size_t)n_hyp * n);
+    // FindFundamental keeps a hypothesis only when currentScore > score (score starts at 0)
+    float bs = 0.f;
+    for (int i = 0; i < n_hyp; i++)
+        if (out_scores[i] > bs) { bs = out_scores[i]; *best = i; }
+    return DR3LK_OK;
+}
+
 }  // extern "C"

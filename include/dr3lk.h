@@ -159,6 +159,16 @@ int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t s
                       int fast_threshold, double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy,
                       int* out_level, float* out_score, int* n_out);
 
+/* f-4: scoring of RANSAC fundamental-matrix hypotheses -- InitHelper::CheckFundamental (reference
+ * src/initialization.cpp:171-249) for n_hyp matrices at once, as FindFundamental (src/initialization.cpp:81-133)
+ * needs it for its 200 hypotheses.  F21: n_hyp x 9 floats (row-major 3x3, already de-normalised: T2^T * Fn * T1);
+ * pts1 / pts2: n x 2 floats (matched key points of frames 1 and 2); sigma as in the reference (1.0).
+ * out_scores: n_hyp floats; out_inliers: n_hyp x n bytes (may be NULL); *best receives the index FindFundamental would
+ * keep (first hypothesis with the strictly largest score, -1 when every score is <= 0).  The fp32 operations and the
+ * accumulation order over the matches are the reference's, so scores are bit-identical to a scalar evaluation. */
+int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, int n, float sigma,
+                            float* out_scores, uint8_t* out_inliers, int* best);
+
 #ifdef __cplusplus
 }
 #endif

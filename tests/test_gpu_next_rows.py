@@ -93,3 +93,30 @@ def test_fast_detector_parameters_and_occupancy(ctx, dr3):
     p, s, e = ctx.calc_optical_flow_pyr_lk(k0, b, xy.astype(np.float32), xy.astype(np.float32), (30, 30), 4, (3, 1000, 1e-3), dr3.USE_INITIAL_FLOW)
     po, so, eo = oracle.calc_optical_flow_pyr_lk(k0, b, xy.astype(np.float32), xy.astype(np.float32), (30, 30), 4, (3, 1000, 1e-3), 4)
     assert s.sum() >= 100 and np.array_equal(s, so) and np.array_equal(p.view(np.uint32), po.view(np.uint32))
+
+
+def test_score_fundamental_matches_restatement(ctx):
+    """f-4: 200 RANSAC hypotheses scored against the tracked matches, bit-identical to the scalar fp32 evaluation."""
+    rng = np.random.default_rng(33)
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = golden_case("c1_default_21x21")["prev_pts"][:4607]
+    p, s, _ = ctx.calc_optical_flow_pyr_lk(a, b, pts)
+    p1, p2 = pts[s == 1][:546], p[s == 1][:546]
+    # hypotheses: perturbations of a plausible forward-motion F plus a few degenerate ones
+    F0 = np.array([[0, -1e-6, 2e-4], [1e-6, 0, -3e-3], [-2e-4, 3e-3, 0]], np.float32)
+    F = (F0[None] * (1 + 0.3 * rng.standard_normal((200, 3, 3)))).astype(np.float32)
+    F[7] = 0
+    F[11] = np.eye(3, dtype=np.float32)
+    sc, inl, best = ctx.score_fundamental(F, p1, p2, 1.0)
+    esc, einl = postfilter.check_fundamental(F, p1, p2, 1.0)
+    # bit-identical, except that a NaN score (the all-zero hypothesis: 0/0) carries a different payload on the GPU
+    nan = np.isnan(esc)
+    assert nan[7] and np.array_equal(np.isnan(sc), nan)
+    assert np.array_equal(sc[~nan].view(np.uint32), esc[~nan].view(np.uint32)) and np.array_equal(inl, einl)
+    exp_best, bs = -1, np.float32(0)
+    for i in range(200):
+        if esc[i] > bs:
+            bs, exp_best = esc[i], i
+    assert best == exp_best and np.nanmax(sc) > 0
+    sc2, inl2, _ = ctx.score_fundamental(F[:3], p1[:5], p2[:5], 2.0, want_inliers=False)
+    assert inl2 is None and np.array_equal(sc2, postfilter.check_fundamental(F[:3], p1[:5], p2[:5], 2.0)[0])
