@@ -44,7 +44,7 @@ struct Geo {
     static constexpr int NEO = (R + 3) / 4;              // realigned registers per parity
     static constexpr bool RAGGED = (WW % R) != 0;
     static constexpr int WARPS = 4;                      // warps per CTA (each warp is an independent worker)
-    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? 4 : 2;  // register budget: 128 / thread, or 255 for big windows
+    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? 4 : 3;  // measured best: 16 warps/SM at <= 128 registers (21x21), 12 at <= 168 (31x31, 30x30)
     static constexpr int MX = 13, MY = 8;                // search-region margins (x margin is >= MX after alignment)
     static constexpr int J_CH = (WW + 1 + 2 * MX + 15 + 15) / 16;  // 16-B chunks per search-region row
     static constexpr int J_W = J_CH * 16;
