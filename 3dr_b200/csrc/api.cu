@@ -58,8 +58,12 @@ struct PyrLayout {
     int w[kMaxLevels], h[kMaxLevels];
     int pitch[kMaxLevels];   // bytes, 16-B aligned (scratch levels)
     int dpitch[kMaxLevels];  // ints, 16-B aligned
-    size_t img_bytes[kMaxLevels];   // per image
-    size_t der_ints[kMaxLevels];    // per image
+    size_t img_bytes[kMaxLevels];   // per image, aprons included
+    size_t der_ints[kMaxLevels];    // per image, aprons included
+    // Aprons (dr3lk_internal.cuh) around every level when the window has a specialised LK kernel, else 0; with aprons
+    // level 0 is an apron-carrying scratch copy too.  img_org / der_org: offset of pixel (0, 0) inside one image.
+    int ax = 0, ay = 0, dax = 0;
+    size_t img_org[kMaxLevels], der_org[kMaxLevels];
 };
 
 PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
@@ -67,12 +71,15 @@ PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
     PyrLayout P;
     int ws[kMaxLevels], hs[kMaxLevels];
     P.ml = dr3lk_lk_level_sizes(w, h, win_w, win_h, std::min(max_level, kMaxLevels - 1), ws, hs);
+    if (lk_fast_supported(win_w, win_h)) { P.ax = kApronX; P.ay = apron_y(win_h); P.dax = deriv_apron_x(win_w); }
     for (int l = 0; l <= P.ml; l++) {
         P.w[l] = ws[l]; P.h[l] = hs[l];
-        P.pitch[l] = align_up(ws[l], 16);
-        P.dpitch[l] = align_up(ws[l], 4);
-        P.img_bytes[l] = (size_t)P.pitch[l] * hs[l];
-        P.der_ints[l] = (size_t)P.dpitch[l] * hs[l];
+        P.pitch[l] = align_up(ws[l] + 2 * P.ax, 16);
+        P.dpitch[l] = align_up(ws[l] + 2 * P.dax, 4);
+        P.img_bytes[l] = (size_t)P.pitch[l] * (hs[l] + 2 * P.ay);
+        P.der_ints[l] = (size_t)P.dpitch[l] * (hs[l] + 2 * P.ay);
+        P.img_org[l] = (size_t)P.ay * P.pitch[l] + P.ax;
+        P.der_org[l] = (size_t)P.ay * P.dpitch[l] + P.dax;
     }
     return P;
 }
@@ -80,12 +87,23 @@ PyrLayout make_layout(int w, int h, int win_w, int win_h, int max_level)
 // Device scratch for one batch of frame pairs: Gaussian levels >= 1 of both frames, derivatives of the previous
 // frame at every level, optionally level-0 copies (host-buffer entry points), and the point arrays.
 struct Workspace {
-    DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs, pair_idx, al_prev, al_next, counter;
+    DevBuf pyr_prev, pyr_next, deriv, lvl0_prev, lvl0_next, pts, offs, pair_idx, counter;
     int epoch = 0;  // LK launches on this workspace (selects the work counter)
+    // The derivative aprons are zeros that no kernel ever writes: they are cleared once per (allocation, layout).
+    struct DerivSig {
+        const void* p = nullptr;
+        size_t cap = 0;
+        int w = 0, h = 0, win_w = 0, win_h = 0, ml = 0, batch = 0;
+        bool operator==(const DerivSig& o) const
+        {
+            return p == o.p && cap == o.cap && w == o.w && h == o.h && win_w == o.win_w && win_h == o.win_h && ml == o.ml && batch == o.batch;
+        }
+    } deriv_sig;
     void release()
     {
         pyr_prev.release(); pyr_next.release(); deriv.release(); lvl0_prev.release(); lvl0_next.release(); pts.release();
-        offs.release(); pair_idx.release(); al_prev.release(); al_next.release(); counter.release();
+        offs.release(); pair_idx.release(); counter.release();
+        deriv_sig = DerivSig();
     }
 };
 
@@ -154,16 +172,19 @@ int check_lk_args(dr3lk_ctx* ctx, int w, int h, const LKArgs& a)
     return DR3LK_OK;
 }
 
-// Builds both Gaussian pyramids and the Scharr derivatives for `batch` pairs.  prev0/next0: device level-0 images.
-// Fills `lk` level descriptors.  Scratch comes from `W`.
-int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, int pitch0,
-                   size_t stride0, int batch, const PyrLayout& P, LKParams& lk)
+// Builds both Gaussian pyramids and the Scharr derivatives for `batch` pairs.  prev0/next0: device level-0 images (any
+// alignment).  With aprons (P.ax > 0) level 0 is first copied into its apron-carrying scratch image.  Fills the `lk`
+// level descriptors (pointers at pixel (0, 0)) and lk.fast_ok.  Scratch comes from `W`.
+int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, size_t pitch0,
+                   size_t stride0, int batch, const PyrLayout& P, int win_w, int win_h, LKParams& lk)
 {
-    if (stride0 >= (1ull << 32) || P.der_ints[0] >= (1ull << 32)) return fail(ctx, DR3LK_E_SIZE, "images of 4 GiB or more are not supported");
+    const bool apr = P.ax > 0;
+    if (stride0 >= (1ull << 32) || P.img_bytes[0] >= (1ull << 32) || P.der_ints[0] >= (1ull << 32) || pitch0 >= (1ull << 31))
+        return fail(ctx, DR3LK_E_SIZE, "images of 4 GiB or more are not supported");
     size_t pyr_bytes = 0, der_ints = 0;
     size_t lvl_off[kMaxLevels] = {0}, der_off[kMaxLevels] = {0};
     for (int l = 0; l <= P.ml; l++) {
-        if (l >= 1) { lvl_off[l] = pyr_bytes; pyr_bytes += P.img_bytes[l] * batch; }
+        if (l >= 1 || apr) { lvl_off[l] = pyr_bytes; pyr_bytes += P.img_bytes[l] * batch; }
         der_off[l] = der_ints; der_ints += P.der_ints[l] * batch;
     }
     cudaSetDevice(ctx->device);
@@ -172,27 +193,42 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         CU_TRY(ctx, W.pyr_next.reserve(pyr_bytes));
     }
     CU_TRY(ctx, W.deriv.reserve(der_ints * sizeof(int)));
+    if (apr) {
+        Workspace::DerivSig sig;
+        sig.p = W.deriv.p; sig.cap = W.deriv.cap;
+        sig.w = P.w[0]; sig.h = P.h[0]; sig.win_w = win_w; sig.win_h = win_h; sig.ml = P.ml; sig.batch = batch;
+        if (!(sig == W.deriv_sig)) {
+            CU_TRY(ctx, cudaMemsetAsync(W.deriv.p, 0, der_ints * sizeof(int), stream));
+            W.deriv_sig = sig;
+        }
+    } else {
+        W.deriv_sig = Workspace::DerivSig();  // an apron-less layout is about to overwrite the zeros
+    }
 
     for (int l = 0; l <= P.ml; l++) {
         LevelDesc& d = lk.lv[l];
         d.w = P.w[l]; d.h = P.h[l];
-        if (l == 0) {
+        if (l == 0 && !apr) {
             d.prev = prev0; d.next = next0;
-            d.pitch_p = d.pitch_n = pitch0;
+            d.pitch_p = d.pitch_n = (int)pitch0;
             d.prev_stride = d.next_stride = (unsigned)stride0;
         } else {
-            d.prev = (const uint8_t*)W.pyr_prev.p + lvl_off[l];
-            d.next = (const uint8_t*)W.pyr_next.p + lvl_off[l];
+            d.prev = (const uint8_t*)W.pyr_prev.p + lvl_off[l] + P.img_org[l];
+            d.next = (const uint8_t*)W.pyr_next.p + lvl_off[l] + P.img_org[l];
             d.pitch_p = d.pitch_n = P.pitch[l];
             d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
         }
-        d.deriv = (const int*)W.deriv.p + der_off[l];
+        d.deriv = (const int*)W.deriv.p + der_off[l] + P.der_org[l];
         d.dpitch = P.dpitch[l];
         d.deriv_stride = (unsigned)P.der_ints[l];
     }
     lk.max_level = P.ml;
+    lk.fast_ok = apr ? 1 : 0;
 
     Launch L{stream, cudaSuccess, 0};
+    if (apr)
+        launch_pad_level0(L, prev0, next0, pitch0, stride0, const_cast<uint8_t*>(lk.lv[0].prev), const_cast<uint8_t*>(lk.lv[0].next), P.pitch[0],
+                          P.img_bytes[0], P.w[0], P.h[0], P.ax, P.ay, batch, next0 ? batch : 0);
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = lk.lv[l];
         const bool down = l < P.ml;
@@ -201,8 +237,9 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         a.prev_src_stride = s.prev_stride; a.next_src_stride = s.next_stride;
         a.w = s.w; a.h = s.h; a.src_pitch = s.pitch_p;
         a.deriv = const_cast<int*>(s.deriv); a.dpitch = s.dpitch; a.deriv_stride = s.deriv_stride;
-        a.n_prev = batch; a.n_next = down ? batch : 0;
+        a.n_prev = batch; a.n_next = (down && next0) ? batch : 0;
         a.down = down;
+        a.dst_apron_x = P.ax; a.dst_apron_y = P.ay;
         if (down) {
             a.prev_dst = const_cast<uint8_t*>(lk.lv[l + 1].prev); a.next_dst = const_cast<uint8_t*>(lk.lv[l + 1].next);
             a.prev_dst_stride = lk.lv[l + 1].prev_stride; a.next_dst_stride = lk.lv[l + 1].next_stride;
@@ -287,31 +324,9 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
         for (int i = 0; i < 3; i++) CU_TRY(ctx, cudaEventCreate(&pr.e[i]));
         CU_TRY(ctx, cudaEventRecord(pr.e[0], stream));
     }
-    // The specialised kernels stage image rows with 16-byte loads: give them a 16-B aligned level 0 when the
-    // caller's layout is not (e.g. continuous 1241-wide images).
-    const bool want_fast = lk_fast_supported(a.win_w, a.win_h);
-    auto aligned16 = [](const void* p, size_t a1, size_t a2) { return ((reinterpret_cast<uintptr_t>(p) | a1 | a2) & 15) == 0; };
-    if (want_fast && !(aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride))) {
-        const int ap = align_up(w, 16);
-        const size_t ab = (size_t)ap * h;
-        CU_TRY(ctx, W.al_prev.reserve(ab * batch));
-        CU_TRY(ctx, W.al_next.reserve(ab * batch));
-        if (image_stride == pitch * (size_t)h) {
-            CU_TRY(ctx, cudaMemcpy2DAsync(W.al_prev.p, ap, prev_dev, pitch, w, (size_t)h * batch, cudaMemcpyDeviceToDevice, stream));
-            CU_TRY(ctx, cudaMemcpy2DAsync(W.al_next.p, ap, next_dev, pitch, w, (size_t)h * batch, cudaMemcpyDeviceToDevice, stream));
-        } else {
-            for (int b = 0; b < batch; b++) {
-                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.al_prev.p + ab * b, ap, prev_dev + image_stride * b, pitch, w, h, cudaMemcpyDeviceToDevice, stream));
-                CU_TRY(ctx, cudaMemcpy2DAsync((uint8_t*)W.al_next.p + ab * b, ap, next_dev + image_stride * b, pitch, w, h, cudaMemcpyDeviceToDevice, stream));
-            }
-        }
-        prev_dev = (const uint8_t*)W.al_prev.p; next_dev = (const uint8_t*)W.al_next.p;
-        pitch = ap; image_stride = ab;
-    }
-    int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, (int)pitch, image_stride, batch, P, lk);
+    int rc = build_pyramids(ctx, W, stream, prev_dev, next_dev, pitch, image_stride, batch, P, a.win_w, a.win_h, lk);
     if (rc != DR3LK_OK) return rc;
     if (ctx->profiling) CU_TRY(ctx, cudaEventRecord(pr.e[1], stream));
-    lk.fast_ok = aligned16(prev_dev, pitch, image_stride) && aligned16(next_dev, pitch, image_stride);
     rc = run_tracking(ctx, W, stream, lk, batch, prev_pts_dev, next_pts_dev, status_dev, err_dev, pts_offset, pts_offset_dev, n_total,
                       stats_dev, a);
     if (ctx->profiling) {
@@ -730,8 +745,8 @@ int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, siz
     LKParams lk;
     memset(&lk, 0, sizeof(lk));
     PyrLayout P = make_layout(w, h, win_w, win_h, max_level);
-    // the "next" pyramid of build_pyramids is pointed at the same image; only the prev outputs are read back
-    rc = build_pyramids(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, (const uint8_t*)W.lvl0_prev.p, pitch0, img_bytes, 1, P, lk);
+    // previous-frame side only (next0 == nullptr): Gaussian levels + derivatives
+    rc = build_pyramids(ctx, W, st, (const uint8_t*)W.lvl0_prev.p, nullptr, pitch0, img_bytes, 1, P, win_w, win_h, lk);
     if (rc != DR3LK_OK) return rc;
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& d = lk.lv[l];
@@ -778,23 +793,34 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
     p->img = ctx->take(img_total);
     p->deriv = ctx->take(der_total * sizeof(int));
+    const int pitch0 = align_up(w, 16);
+    const size_t l0_bytes = (size_t)pitch0 * h;
     cudaError_t e = p->img.reserve(img_total);
     if (e == cudaSuccess) e = p->deriv.reserve(der_total * sizeof(int));
-    if (e == cudaSuccess) e = ctx->pinned.reserve(P.img_bytes[0]);
+    if (e == cudaSuccess) e = ctx->pinned.reserve(l0_bytes);
+    if (e == cudaSuccess && P.ax > 0) e = ctx->ws.lvl0_prev.reserve(l0_bytes);
     if (e != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, e, "pyramid_create: allocation"); }
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * P.pitch[0], img + (size_t)y * step, (size_t)w);
-    e = cudaMemcpyAsync(p->img.p, hp, P.img_bytes[0], cudaMemcpyHostToDevice, st);
-    Launch L{st, e, 0};
+    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
     for (int l = 0; l <= P.ml; l++) {
         LevelDesc& d = p->lv[l];
         d.w = P.w[l]; d.h = P.h[l];
-        d.prev = d.next = (const uint8_t*)p->img.p + ioff[l];
+        d.prev = d.next = (const uint8_t*)p->img.p + ioff[l] + P.img_org[l];
         d.pitch_p = d.pitch_n = P.pitch[l];
         d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
-        d.deriv = (const int*)p->deriv.p + doff[l];
+        d.deriv = (const int*)p->deriv.p + doff[l] + P.der_org[l];
         d.dpitch = P.dpitch[l];
         d.deriv_stride = (unsigned)P.der_ints[l];
+    }
+    Launch L{st, cudaSuccess, 0};
+    if (P.ax > 0) {
+        // level 0 lands in scratch and is copied into its apron-carrying image; the derivative aprons are zeros
+        L.err = cudaMemcpyAsync(ctx->ws.lvl0_prev.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);
+        if (L.err == cudaSuccess) L.err = cudaMemsetAsync(p->deriv.p, 0, der_total * sizeof(int), st);
+        launch_pad_level0(L, (const uint8_t*)ctx->ws.lvl0_prev.p, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr,
+                          P.pitch[0], P.img_bytes[0], w, h, P.ax, P.ay, 1, 0);
+    } else {
+        L.err = cudaMemcpyAsync(p->img.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);  // P.pitch[0] == pitch0 without aprons
     }
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = p->lv[l];
@@ -804,6 +830,7 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
         pa.deriv = const_cast<int*>(s.deriv); pa.dpitch = s.dpitch; pa.deriv_stride = s.deriv_stride;
         pa.n_prev = 1; pa.n_next = 0;
         pa.down = l < P.ml;
+        pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
         if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
         launch_pyr_level(L, pa);
     }
@@ -856,7 +883,7 @@ int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* p
         lk.lv[l].next_stride = next->lv[l].prev_stride;
     }
     lk.max_level = ml;
-    lk.fast_ok = 1;  // pyramid buffers are always 16-B aligned
+    lk.fast_ok = prev->P.ax > 0;  // pyramid objects carry the aprons whenever the window has a specialised kernel
     const size_t n8 = align_up_sz(8 * (size_t)n, 16);
     const size_t o_prev = 0, o_offs = n8, o_next = o_offs + 16, o_err = o_next + n8, o_status = o_err + align_up_sz(4 * (size_t)n, 16);
     const size_t total = o_status + align_up_sz((size_t)n, 16);

@@ -10,7 +10,17 @@ namespace dr3lk {
 constexpr int kMaxLevels = DR3LK_MAX_LEVELS;
 constexpr int W_BITS = 14;  // OpenCV lkpyramid.cpp fixed-point weight bits
 
-// One pyramid level of a batch of frame pairs, as the LK kernels see it.
+// Apron ("padding") around every pyramid level the specialised LK kernels read.  Like OpenCV's
+// buildOpticalFlowPyramid (level images padded by winSize with BORDER_REFLECT_101, derivatives with BORDER_CONSTANT 0,
+// SURVEY.md Appendix A.2/A.3) every level image carries kApronX columns / apron_y(win_h) rows of reflected pixels on
+// each side and every derivative level an apron of zeros, so the LK kernels stage windows and search regions with plain
+// 16-byte row copies: no index reflection, no zero-fill predicates, no byte-wise border path.
+constexpr int kApronX = 32;                                           // bytes; a multiple of 16 keeps x = 0 16-B aligned
+__host__ __device__ constexpr int apron_y(int win_h) { return win_h + 1; }                    // rows
+__host__ __device__ constexpr int deriv_apron_x(int win_w) { return (win_w + 1 + 3) / 4 * 4; }  // ints (16-B multiple)
+
+// One pyramid level of a batch of frame pairs, as the LK kernels see it.  prev / next / deriv point at pixel (0, 0) of
+// image 0; with lk.fast_ok the aprons above exist around every image (negative coordinates are addressable).
 struct LevelDesc {
     const uint8_t* prev;   // [batch][h][pitch_p]  level image of the previous frame
     const uint8_t* next;   // [batch][h][pitch_n]
@@ -32,7 +42,7 @@ struct LKParams {
     uint32_t* stats;       // may be null
     const int* pair_idx;   // device, one frame-pair index per point (used when uniform_n == 0)
     int uniform_n;         // > 0: every pair has exactly this many points (pair = point / uniform_n)
-    int fast_ok;           // all level images / derivatives are 16-B aligned (base, pitch, stride)
+    int fast_ok;           // every level is 16-B aligned (origin, pitch, stride) and carries the aprons (kApronX, apron_y, deriv_apron_x)
     int* work_counter;     // two device ints (zero-initialised): counter [work_epoch & 1] feeds the persistent warps of
     int work_epoch;        // this launch, which also re-zeroes the other one for the next launch (no memset per call)
     float eps2_lo, eps2_hi; // fp32 brackets of eps2: below lo / above hi the fp32 estimate of |delta|^2 decides
@@ -65,8 +75,14 @@ struct PyrLevelArgs {
     int w, h, src_pitch, dst_pitch, dpitch;
     int n_prev, n_next;
     bool down;
+    int dst_apron_x, dst_apron_y;  // > 0: also write the REFLECT_101 apron of the down-sampled level
 };
 void launch_pyr_level(Launch& L, const PyrLevelArgs& a);
+// Level 0 into its apron-carrying scratch copy: dst(x, y) = src(reflect101(x), reflect101(y)) for -ax <= x < w + ax,
+// -ay <= y < h + ay, for n_a images of set A followed by n_b images of set B (same geometry; one launch serves the previous
+// and the next frames).  dst_* point at pixel (0, 0) of image 0 and are 16-B aligned (origin, pitch, stride); src is arbitrary.
+void launch_pad_level0(Launch& L, const uint8_t* src_a, const uint8_t* src_b, size_t src_pitch, size_t src_stride, uint8_t* dst_a,
+                       uint8_t* dst_b, int dst_pitch, size_t dst_stride, int w, int h, int ax, int ay, int n_a, int n_b);
 void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
                      uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding);
 

@@ -4,9 +4,10 @@
 //
 //   * Per level the warp stages three regions in shared memory with 16-byte row-coalesced loads (every image row of
 //     the window is touched once per level): the template window of the previous image (u8), its Scharr derivatives
-//     (packed s16x2) and a search region of the next image (window + >= 13 px margin in x, 8 px in y).  Borders are
-//     resolved while staging (REFLECT_101 index reflection for images, zeros for derivatives), so the compute code
-//     never branches on borders.  The search region is re-staged only when the window leaves it.
+//     (packed s16x2) and a search region of the next image (window + >= 11 px margin in x, 8 px in y).  Every level
+//     carries an apron (reflected pixels / zero derivatives, dr3lk_internal.cuh), so staging is plain 16-byte row
+//     copies (cp.async) with one address computation per region and neither staging nor compute ever branches on
+//     borders.  The search region is re-staged only when the window leaves it.
 //   * The window is cut into runs of R consecutive pixels of one row; each lane owns NRUN runs.  A run's R+1 source
 //     bytes of two rows are fetched as 3-4 aligned 32-bit shared loads and realigned with PRMT, and the 14-bit
 //     bilinear blend is two IDP.2A (dp2a: 2 x (s16 weight * u8 pixel)) per pixel instead of four IMADs.
@@ -59,9 +60,11 @@ struct Geo {
     static constexpr int I_WORDS = I_PW * (WH + 1) + 4;
     static constexpr int D_ZERO = D_PW * (WH + 1);       // two rows of zeros for runs that do not exist
     static constexpr int D_WORDS = D_PW * (WH + 3) + 4;
-    // smallest level the kernel accepts: one reflection must suffice for every row / column staging can touch
-    static constexpr int MIN_H = WH + MY + 2;
-    static constexpr int MIN_W = (J_W > I_W ? J_W : I_W) + 1;
+    static constexpr int PX = kApronX, PY = apron_y(WH), DPX = deriv_apron_x(WW);  // aprons of every level (bytes, rows, ints)
+    // smallest level the kernel accepts: the aprons are filled by ONE reflection of the level
+    static constexpr int MIN_H = PY + 1;
+    static constexpr int MIN_W = PX + 1;
+    static_assert(PX >= WW + 1 && PX % 16 == 0 && DPX >= WW + 1 && DPX % 4 == 0, "aprons must cover a window hanging over the border");
     static constexpr int WARP_WORDS = (J_WORDS + I_WORDS + D_WORDS + 3) / 4 * 4;
     static_assert((long long)NRUN * R * 8160LL * 4080LL < 2147483647LL, "per-lane int32 partial sums would overflow");
     static_assert(J_W >= WW + 1 + MX + MX + 15, "search region too narrow");
@@ -153,14 +156,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// REFLECT_101 for -(len-1) <= p <= 2*len-2 (one reflection).  launch_lk_fast only takes levels large enough that
-// every row/column the staging code touches is in that range (Geo::MIN_W / MIN_H); smaller images use lk_generic.
-__device__ __forceinline__ int reflect_once(int p, int len)
-{
-    const int a = abs(p);
-    return min(a, 2 * len - 2 - a);
-}
-
 __host__ __device__ constexpr int pow2_at_least(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
 
 template <typename G>
@@ -168,113 +163,52 @@ struct Tracker {
     static constexpr int WW = G::WW, WH = G::WH;
 
     // NROWS rows of CH 16-byte chunks, LPR (power of two) lanes per row: global -> shared with cp.async (LDGSTS: no
-    // registers, completion tracked per commit group).  `base` points at the first chunk of image row 0; row r of the
-    // region is image row y0 + r, reflected into the image (REFLECT_101) or, with ZERO_OUTSIDE, zero-filled when it
-    // lies outside (src-size 0; the address is still the reflected, valid row).
-    template <int NROWS, int CH, int PITCH_BYTES, bool ZERO_OUTSIDE>
-    static __device__ __forceinline__ void stage_rows(uint8_t* sb, int lane, const uint8_t* base, int pitch_bytes, int y0, int h)
+    // registers, completion tracked per commit group).  `g` points at the first chunk of the first row; thanks to the
+    // aprons every row is a plain copy.
+    template <int NROWS, int CH, int PITCH_BYTES>
+    static __device__ __forceinline__ void stage_rows(void* region, int lane, const uint8_t* g, int pitch_bytes)
     {
         constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = (NROWS + RPR - 1) / RPR;
         const int ch = lane & (LPR - 1), rr = lane / LPR;
-        if (ch >= CH) return;
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sb) + rr * PITCH_BYTES + ch * 16;
-        const uint8_t* cbase = base + ch * 16;
+        if (CH < LPR && ch >= CH) return;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(region) + rr * PITCH_BYTES + ch * 16;
+        g += (long long)rr * pitch_bytes + ch * 16;
+        const long long step = (long long)RPR * pitch_bytes;
 #pragma unroll
         for (int i = 0; i < ROUNDS; i++) {
-            const int row = rr + i * RPR;
-            if ((i + 1) * RPR > NROWS && row >= NROWS) break;
-            const int gy = y0 + row;
-            const uint8_t* g = cbase + (long long)reflect_once(gy, h) * pitch_bytes;
-            if (ZERO_OUTSIDE) {
-                const int nbytes = (unsigned)gy < (unsigned)h ? 16 : 0;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g), "r"(nbytes) : "memory");
-            } else {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g) : "memory");
-            }
+            if ((i + 1) * RPR > NROWS && rr + i * RPR >= NROWS) break;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g) : "memory");
+            g += step;
         }
     }
 
     // ---- staging -------------------------------------------------------------------------------------------
-    // All stage_* functions only ISSUE the copies (cp.async, or plain stores on the rare byte-wise border path); the
-    // caller commits the group, waits for it and __syncwarp()s before any lane reads the region.
-    // Search region of the next image around window origin (inx, iny).  Sets rx0/ry0 and the valid x range.
-    static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int w, int h, int inx,
-                                                   int iny, int lane, int& rx0, int& ry0, int& vspan)
+    // All stage_* functions only ISSUE the copies; the caller commits the group, waits for it and __syncwarp()s
+    // before any lane reads the region.  Coordinates are relative to pixel (0, 0) of the level; the aprons make
+    // x in [-PX, w + PX) and y in [-PY, h + PY) addressable.
+    // Search region of the next image around window origin (inx, iny): J_W x J_H bytes from (rx0, ry0); window origins
+    // rx0 .. rx0 + J_W - (WW+1), ry0 .. ry0 + 2*MY are inside it.
+    static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int h, int inx, int iny, int lane,
+                                                   int& rx0, int& ry0)
     {
-        ry0 = iny - G::MY;
-        uint8_t* sb = reinterpret_cast<uint8_t*>(sJ);
-        if (inx >= 0 && inx + WW < w) {
-            int x0 = (inx - G::MX) & ~15;
-            x0 = max(0, min(x0, pitch - G::J_W));
-            rx0 = x0;
-            vspan = min(x0 + G::J_W, w) - x0 - (WW + 1);  // window origins rx0 .. rx0 + vspan are inside the region
-            stage_rows<G::J_H, G::J_CH, G::J_PW * 4, false>(sb, lane, img + x0, pitch, ry0, h);
-        } else {
-            // window touches the left/right border: byte-wise with reflection in x and y
-            rx0 = inx - (G::J_W - (WW + 1)) / 2;
-            vspan = G::J_W - (WW + 1);
-            int gx[(G::J_W + 31) / 32];
-#pragma unroll
-            for (int c = 0; c < (G::J_W + 31) / 32; c++) gx[c] = reflect_once(rx0 + lane + 32 * c, w);
-#pragma unroll 2
-            for (int row = 0; row < G::J_H; row++) {
-                const uint8_t* src = img + (long long)reflect_once(ry0 + row, h) * pitch;
-#pragma unroll
-                for (int c = 0; c < (G::J_W + 31) / 32; c++)
-                    if (lane + 32 * c < G::J_W) sb[row * (G::J_PW * 4) + lane + 32 * c] = __ldg(src + gx[c]);
-            }
-        }
+        rx0 = max(-G::PX, min((inx - G::MX) & ~15, pitch - G::PX - G::J_W));
+        ry0 = max(-G::PY, min(iny - G::MY, h + G::PY - G::J_H));
+        stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sJ, lane, img + (long long)ry0 * pitch + rx0, pitch);
     }
+    // first staged column of the template window / its derivatives for window origin x = ipx
+    static __device__ __forceinline__ int x0_I(int ipx, int pitch) { return min(ipx & ~15, pitch - G::PX - G::I_W); }
+    static __device__ __forceinline__ int x0_D(int ipx, int dpitch) { return min(ipx & ~3, dpitch - G::DPX - G::D_CH * 4); }
 
-    // Template window of the previous image: WH+1 rows from ipy, bytes from x0 (returned) .. x0 + I_W
-    static __device__ __forceinline__ int stage_I(unsigned* sI, const uint8_t* __restrict__ img, int pitch, int w, int h, int ipx, int ipy,
-                                                  int lane)
+    // Template window of the previous image: WH+1 rows from ipy, I_W bytes from x0_I
+    static __device__ __forceinline__ void stage_I(unsigned* sI, const uint8_t* __restrict__ img, int pitch, int ipx, int ipy, int lane)
     {
-        uint8_t* sb = reinterpret_cast<uint8_t*>(sI);
-        int x0;
-        if (ipx >= 0 && ipx + WW < w) {
-            x0 = min(ipx & ~15, pitch - G::I_W);
-            stage_rows<WH + 1, G::I_CH, G::I_PW * 4, false>(sb, lane, img + x0, pitch, ipy, h);
-        } else {
-            x0 = ipx;
-            int gx[(G::I_W + 31) / 32];
-#pragma unroll
-            for (int c = 0; c < (G::I_W + 31) / 32; c++) gx[c] = reflect_once(x0 + lane + 32 * c, w);
-#pragma unroll 2
-            for (int row = 0; row <= WH; row++) {
-                const uint8_t* src = img + (long long)reflect_once(ipy + row, h) * pitch;
-#pragma unroll
-                for (int c = 0; c < (G::I_W + 31) / 32; c++)
-                    if (lane + 32 * c < G::I_W) sb[row * (G::I_PW * 4) + lane + 32 * c] = __ldg(src + gx[c]);
-            }
-        }
-        return x0;
+        stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sI, lane, img + (long long)ipy * pitch + x0_I(ipx, pitch), pitch);
     }
-
-    // Scharr derivatives of the template window (zero outside the image): WH+1 rows, words from x0 (returned)
-    static __device__ __forceinline__ int stage_D(unsigned* sD, const int* __restrict__ der, int dpitch, int w, int h, int ipx, int ipy,
-                                                  int lane)
+    // Scharr derivatives of the template window (the apron holds the zeros outside the image): WH+1 rows, D_CH*4 words
+    static __device__ __forceinline__ void stage_D(unsigned* sD, const int* __restrict__ der, int dpitch, int ipx, int ipy, int lane)
     {
-        int x0;
-        if (ipx >= 0 && ipx + WW < w) {
-            x0 = min(ipx & ~3, dpitch - G::D_CH * 4);
-            stage_rows<WH + 1, G::D_CH, G::D_PW * 4, true>(reinterpret_cast<uint8_t*>(sD), lane, reinterpret_cast<const uint8_t*>(der + x0),
-                                                          dpitch * 4, ipy, h);
-        } else {
-            x0 = ipx;
-#pragma unroll 2
-            for (int row = 0; row <= WH; row++) {
-                const int gy = ipy + row;
-                const bool yin = (unsigned)gy < (unsigned)h;
-                if (lane < G::D_CH * 4) {
-                    const int gx = x0 + lane;
-                    unsigned v = 0;
-                    if (yin && (unsigned)gx < (unsigned)w) v = (unsigned)__ldg(der + (long long)gy * dpitch + gx);
-                    sD[row * G::D_PW + lane] = v;
-                }
-            }
-        }
-        return x0;
+        stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(sD, lane, reinterpret_cast<const uint8_t*>(der + (long long)ipy * dpitch + x0_D(ipx, dpitch)),
+                                                 dpitch * 4);
     }
 };
 
@@ -330,8 +264,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         float fx, fy;
         if (!template_origin(pp, level, ipx, ipy, fx, fy)) return;
         const LevelDesc& L = P.lv[level];
-        T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, L.w, L.h, ipx, ipy, lane);
-        T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, L.w, L.h, ipx, ipy, lane);
+        T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, ipx, ipy, lane);
+        T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, ipx, ipy, lane);
     };
     auto fetch = [&]() -> int {
         int f = 0;
@@ -382,12 +316,13 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
 
             // search region around the initial estimate: issued now, consumed after the template phase
-            int rx0 = 0, ry0 = 0, vspan = 0;
+            int rx0 = 0, ry0 = 0;
+            constexpr int vspan = G::J_W - (WW + 1);
             bool staged = false;
             if (inb) {
                 const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
                 if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) {
-                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, jx, jy, lane, rx0, ry0, vspan);
+                    T::stage_J(sJ, imgJ, L.pitch_n, h, jx, jy, lane, rx0, ry0);
                     staged = true;
                 }
             }
@@ -403,13 +338,12 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 // ---- template: (I, Ix, Iy) of the window into registers, Gram matrix ----
                 n_templates++;
                 q = make_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
-                const int ox = ipx - min(ipx & ~15, L.pitch_p - G::I_W), oxw = ipx - min(ipx & ~3, L.dpitch - G::D_CH * 4);
-                const bool xin = ipx >= 0 && ipx + WW < w;  // else the byte-wise path staged from x0 = ipx
+                const int ox = ipx - T::x0_I(ipx, L.pitch_p), oxw = ipx - T::x0_D(ipx, L.dpitch);
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
                     RunBytes<R, G::NWD, G::NEO, G::I_PW> rb;
-                    rb.load(sI, iofs[s] + (xin ? ox : 0));
-                    const unsigned* dp = sD + dofs[s] + ((rvalid[s] && xin) ? oxw : 0);
+                    rb.load(sI, iofs[s] + ox);
+                    const unsigned* dp = sD + dofs[s] + (rvalid[s] ? oxw : 0);
                     int tx[R + 1], ty[R + 1], bx[R + 1], by[R + 1];
 #pragma unroll
                     for (int k = 0; k <= R; k++) {
@@ -470,7 +404,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 q = make_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
                 if (!staged || (unsigned)(inx - rx0) > (unsigned)vspan || (unsigned)(iny - ry0) > (unsigned)(2 * G::MY)) {
                     __syncwarp();
-                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, inx, iny, lane, rx0, ry0, vspan);
+                    T::stage_J(sJ, imgJ, L.pitch_n, h, inx, iny, lane, rx0, ry0);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncwarp();
@@ -525,7 +459,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 q = make_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy));
                 if (!staged || (unsigned)(iqx - rx0) > (unsigned)vspan || (unsigned)(iqy - ry0) > (unsigned)(2 * G::MY)) {
                     __syncwarp();
-                    T::stage_J(sJ, imgJ, L.pitch_n, w, h, iqx, iqy, lane, rx0, ry0, vspan);
+                    T::stage_J(sJ, imgJ, L.pitch_n, h, iqx, iqy, lane, rx0, ry0);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncwarp();

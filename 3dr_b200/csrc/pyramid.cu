@@ -37,7 +37,7 @@ struct PyrSet {
 template <bool DOWN>
 __global__ void __launch_bounds__(PYR_THREADS)
 pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int src_aligned, int dst_pitch, int* __restrict__ deriv,
-                 int dpitch, unsigned deriv_stride)
+                 int dpitch, unsigned deriv_stride, int apron_x, int apron_y)
 {
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
     __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
@@ -138,17 +138,78 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
                 const int c = (k == 0 || k == 4) ? 1 : (k == 2 ? 6 : 4);
                 v[0] += c * hv.x; v[1] += c * hv.y; v[2] += c * hv.z; v[3] += c * hv.w;
             }
-            uint8_t* out = o + (long long)gy * dst_pitch + gx;
-            if (gx + 3 < dw && (dst_pitch & 3) == 0) {
-                *reinterpret_cast<unsigned*>(out) = (unsigned)(v[0] >> 8) | ((unsigned)(v[1] >> 8) << 8) | ((unsigned)(v[2] >> 8) << 16) |
-                                                    ((unsigned)(v[3] >> 8) << 24);
-            } else {
+            // the row itself plus its REFLECT_101 images in the apron rows (row g mirrors to -g and to 2(dh-1)-g)
+            int ys[3] = {gy, gy, gy};
+            int ny = 1;
+            if (apron_y > 0) {
+                if (gy >= 1 && gy <= apron_y) ys[ny++] = -gy;
+                const int m = 2 * (dh - 1) - gy;
+                if (gy <= dh - 2 && m <= dh - 1 + apron_y) ys[ny++] = m;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (gx + j < dw) out[j] = (uint8_t)(v[j] >> 8);
+            for (int i = 0; i < 3; i++) {
+                if (i >= ny) break;
+                uint8_t* row = o + (long long)ys[i] * dst_pitch;
+                uint8_t* out = row + gx;
+                if (gx + 3 < dw && (dst_pitch & 3) == 0) {
+                    *reinterpret_cast<unsigned*>(out) = (unsigned)(v[0] >> 8) | ((unsigned)(v[1] >> 8) << 8) | ((unsigned)(v[2] >> 8) << 16) |
+                                                        ((unsigned)(v[3] >> 8) << 24);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (gx + j < dw) out[j] = (uint8_t)(v[j] >> 8);
+                }
+                if (apron_x > 0 && (gx <= apron_x || gx + 3 >= dw - 1 - apron_x)) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int x = gx + j, mx = 2 * (dw - 1) - x;
+                        if (x >= dw) continue;
+                        if (x >= 1 && x <= apron_x) row[-x] = (uint8_t)(v[j] >> 8);
+                        if (x <= dw - 2 && mx <= dw - 1 + apron_x) row[mx] = (uint8_t)(v[j] >> 8);
+                    }
+                }
             }
         }
     }
+}
+
+// Level 0 with its REFLECT_101 apron: one 16-byte destination chunk per thread.  Interior chunks read the source row
+// through aligned 32-bit words realigned with funnel shifts (the caller's rows may have any alignment, e.g. continuous
+// 1241-wide images); apron chunks gather byte-wise through the reflected indices.
+__global__ void __launch_bounds__(128)
+pad_level0_kernel(const uint8_t* __restrict__ src_a, const uint8_t* __restrict__ src_b, long long src_pitch, long long src_stride,
+                  uint8_t* __restrict__ dst_a, uint8_t* __restrict__ dst_b, int dst_pitch, long long dst_stride, int w, int h, int ax, int ay,
+                  int n_a)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c * 16 >= dst_pitch) return;
+    const int x = c * 16 - ax, y = (int)blockIdx.y - ay;
+    const bool set_b = (int)blockIdx.z >= n_a;
+    const int img = set_b ? blockIdx.z - n_a : blockIdx.z;
+    const uint8_t* srow = (set_b ? src_b : src_a) + (long long)img * src_stride + (long long)reflect101(y, h) * src_pitch;
+    uint8_t* dst = set_b ? dst_b : dst_a;
+    uint4 v;
+    if (x >= 0 && x + 16 <= w) {
+        const uint8_t* p = srow + x;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+        const unsigned* pw = reinterpret_cast<const unsigned*>(p - mis);
+        const unsigned w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3);
+        if (mis == 0) {
+            v = make_uint4(w0, w1, w2, w3);
+        } else {
+            const unsigned w4 = __ldg(pw + 4), sh = mis * 8;  // the last word ends inside the word holding byte x + 15
+            v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+    } else {
+        unsigned o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int xx = x + i;
+            if (xx < w + ax) o[i >> 2] |= (unsigned)__ldg(srow + reflect101(xx, w)) << (8 * (i & 3));
+        }
+        v = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)img * dst_stride + (long long)y * dst_pitch + x) = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -185,10 +246,21 @@ void launch_pyr_level(Launch& L, const PyrLevelArgs& a)
     PyrSet B{a.next_src, a.next_dst, a.next_src_stride, a.next_dst_stride};
     if (a.down)
         pyr_level_kernel<true><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                 a.deriv_stride);
+                                                                 a.deriv_stride, a.dst_apron_x, a.dst_apron_y);
     else
         pyr_level_kernel<false><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                  a.deriv_stride);
+                                                                  a.deriv_stride, 0, 0);
+    L.err = cudaGetLastError();
+    L.launches++;
+}
+
+void launch_pad_level0(Launch& L, const uint8_t* src_a, const uint8_t* src_b, size_t src_pitch, size_t src_stride, uint8_t* dst_a,
+                       uint8_t* dst_b, int dst_pitch, size_t dst_stride, int w, int h, int ax, int ay, int n_a, int n_b)
+{
+    if (L.err != cudaSuccess || n_a + n_b <= 0) return;
+    dim3 grid((dst_pitch / 16 + 127) / 128, h + 2 * ay, n_a + n_b);
+    pad_level0_kernel<<<grid, 128, 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b, dst_pitch,
+                                                  (long long)dst_stride, w, h, ax, ay, n_a);
     L.err = cudaGetLastError();
     L.launches++;
 }

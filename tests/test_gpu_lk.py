@@ -71,6 +71,30 @@ def test_lk_small_images_and_borders(ctx):
         _assert_bit_exact(got, exp, (h, w, win))
 
 
+def test_lk_apron_layout_borders_and_layout_changes(ctx):
+    """The specialised kernels read every level through its apron (reflected pixels, zero derivatives): windows hanging
+    over all four borders, levels just above the smallest accepted size, and back-to-back calls whose layouts differ
+    (the zero derivative aprons are cleared per layout) must stay bit-exact."""
+    rng = np.random.default_rng(23)
+    shapes = [(23, 34, (21, 21), 0), (47, 156, (21, 21), 1), (120, 97, (31, 31), 1), (64, 33, (30, 30), 0), (200, 333, (21, 21), 3),
+              (90, 70, (45, 33), 1), (200, 333, (21, 21), 3), (33, 131, (31, 31), 2)]
+    for (h, w, win, ml) in shapes:
+        base = rng.integers(0, 256, (h + 8, w + 8)).astype(np.float32)
+        base = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4
+        a = base[4:4 + h, 4:4 + w].astype(np.uint8)
+        b = base[3:3 + h, 5:5 + w].astype(np.uint8)
+        pts = random_points(rng, w, h, 600, margin=win[0] + 3)
+        # a ring of points hugging the four borders and corners
+        edge = np.array([[x, y] for x in (-0.4, 0.0, 0.6, w / 2, w - 1.3, w - 1.0, w - 0.2) for y in (-0.3, 0.0, 0.7, h / 2, h - 1.4, h - 1.0, h - 0.1)],
+                        np.float32)
+        pts = np.concatenate([pts, edge])
+        init = (pts + rng.normal(0, 3.0, pts.shape)).astype(np.float32)
+        for flags, ini in ((0, None), (4, init)):
+            got = ctx.calc_optical_flow_pyr_lk(a, b, pts, ini, win, ml, (3, 30, 0.01), flags)
+            exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, ini, win, ml, (3, 30, 0.01), flags)
+            _assert_bit_exact(got, exp, (h, w, win, ml, flags))
+
+
 def test_lk_errors_and_empty(ctx, dr3):
     a = load_gray("kitti0.png")
     one = np.zeros((1, 2), np.float32)
