@@ -179,8 +179,9 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
                    size_t stride0, int batch, const PyrLayout& P, int win_w, int win_h, LKParams& lk)
 {
     const bool apr = P.ax > 0;
-    if (stride0 >= (1ull << 32) || P.img_bytes[0] >= (1ull << 32) || P.der_ints[0] >= (1ull << 32) || pitch0 >= (1ull << 31))
-        return fail(ctx, DR3LK_E_SIZE, "images of 4 GiB or more are not supported");
+    // the kernels address inside one level image / derivative image with 32-bit byte offsets
+    if (stride0 >= (1ull << 32) || P.img_bytes[0] >= (1ull << 31) || P.der_ints[0] >= (1ull << 29) || pitch0 >= (1ull << 31))
+        return fail(ctx, DR3LK_E_SIZE, "images of 2 GiB or more (derivatives included) are not supported");
     size_t pyr_bytes = 0, der_ints = 0;
     size_t lvl_off[kMaxLevels] = {0}, der_off[kMaxLevels] = {0};
     for (int l = 0; l <= P.ml; l++) {
@@ -789,6 +790,7 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     p->ctx = ctx; p->w = w; p->h = h; p->win_w = win_w; p->win_h = win_h;
     p->P = make_layout(w, h, win_w, win_h, max_level);
     const PyrLayout& P = p->P;
+    if (P.img_bytes[0] >= (1ull << 31) || P.der_ints[0] >= (1ull << 29)) { delete p; return fail(ctx, DR3LK_E_SIZE, "images of 2 GiB or more (derivatives included) are not supported"); }
     size_t img_total = 0, der_total = 0, ioff[kMaxLevels], doff[kMaxLevels];
     for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
     p->img = ctx->take(img_total);

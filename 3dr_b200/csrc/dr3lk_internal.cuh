@@ -16,7 +16,7 @@ constexpr int W_BITS = 14;  // OpenCV lkpyramid.cpp fixed-point weight bits (SUR
 // each side and every derivative level an apron of zeros, so the LK kernels stage windows and search regions with plain
 // 16-byte row copies: no index reflection, no zero-fill predicates, no byte-wise border path.
 constexpr int kApronX = 32;                                           // bytes; a multiple of 16 keeps x = 0 16-B aligned
-__host__ __device__ constexpr int apron_y(int win_h) { return win_h + 1; }                    // rows
+__host__ __device__ constexpr int apron_y(int win_h) { return win_h + 4; }                    // rows: window + 1, + staging slack
 __host__ __device__ constexpr int deriv_apron_x(int win_w) { return (win_w + 1 + 3) / 4 * 4; }  // ints (16-B multiple)
 
 // One pyramid level of a batch of frame pairs, as the LK kernels see it.  prev / next / deriv point at pixel (0, 0) of

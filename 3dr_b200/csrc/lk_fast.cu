@@ -35,6 +35,10 @@ constexpr int pitch_words_for(int need)  // smallest p >= need with p % 8 == 4: 
     return p;
 }
 
+__host__ __device__ constexpr int pow2_at_least(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
+// rows a region of `rows` x `ch` 16-byte chunks occupies when staged in whole rounds of 32 lanes
+constexpr int staged_rows(int rows, int ch) { return (rows + 32 / pow2_at_least(ch) - 1) / (32 / pow2_at_least(ch)) * (32 / pow2_at_least(ch)); }
+
 template <int WW_, int WH_, int R_>
 struct Geo {
     static constexpr int WW = WW_, WH = WH_, R = R_;
@@ -45,7 +49,10 @@ struct Geo {
     static constexpr int NEO = (R + 3) / 4;              // realigned registers per parity
     static constexpr bool RAGGED = (WW % R) != 0;
     static constexpr int WARPS = 4;                      // warps per CTA (each warp is an independent worker)
-    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? 4 : 3;  // measured best: 16 warps/SM at <= 128 registers (21x21), 12 at <= 168 (31x31, 30x30)
+#ifndef DR3LK_BLOCKS_SMALL
+#define DR3LK_BLOCKS_SMALL 4
+#endif
+    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? DR3LK_BLOCKS_SMALL : 3;  // measured best: 16 warps/SM at <= 128 registers (21x21), 12 at <= 168 (31x31, 30x30)
     static constexpr int MX = 13, MY = 8;                // search-region margins (x margin is >= MX after alignment)
     static constexpr int J_CH = (WW + 1 + 2 * MX + 15 + 15) / 16;  // 16-B chunks per search-region row
     static constexpr int J_W = J_CH * 16;
@@ -56,11 +63,15 @@ struct Geo {
     static constexpr int I_PW = pitch_words_for(I_CH * 4);
     static constexpr int D_CH = (WW + 1 + 3 + 3) / 4;    // chunks of 4 derivative words
     static constexpr int D_PW = pitch_words_for(D_CH * 4);
-    static constexpr int J_WORDS = J_PW * J_H + 4;       // +4: realignment may read one word past the last row
-    static constexpr int I_WORDS = I_PW * (WH + 1) + 4;
-    static constexpr int D_ZERO = D_PW * (WH + 1);       // two rows of zeros for runs that do not exist
-    static constexpr int D_WORDS = D_PW * (WH + 3) + 4;
+    // Staging copies whole rounds of 32 lanes (no partial round, no idle-lane branch): regions are rounded up to whole
+    // rounds of rows; the surplus rows are copied (the apron makes them addressable) and never read.
+    static constexpr int J_ROWS = staged_rows(J_H, J_CH), I_ROWS = staged_rows(WH + 1, I_CH), D_ROWS = staged_rows(WH + 1, D_CH);
+    static constexpr int J_WORDS = J_PW * J_ROWS + 4;    // +4: realignment may read one word past the last row
+    static constexpr int I_WORDS = I_PW * I_ROWS + 4;
+    static constexpr int D_ZERO = D_PW * D_ROWS;         // two rows of zeros for runs that do not exist
+    static constexpr int D_WORDS = D_PW * (D_ROWS + 2) + 4;
     static constexpr int PX = kApronX, PY = apron_y(WH), DPX = deriv_apron_x(WW);  // aprons of every level (bytes, rows, ints)
+    static_assert(PY >= I_ROWS && PY >= D_ROWS && PY >= J_ROWS - 2 * MY, "apron rows must cover the rounded-up staging");
     // smallest level the kernel accepts: the aprons are filled by ONE reflection of the level
     static constexpr int MIN_H = PY + 1;
     static constexpr int MIN_W = PX + 1;
@@ -156,27 +167,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__host__ __device__ constexpr int pow2_at_least(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : (v <= 16 ? 16 : 32)))); }
-
 template <typename G>
 struct Tracker {
     static constexpr int WW = G::WW, WH = G::WH;
 
-    // NROWS rows of CH 16-byte chunks, LPR (power of two) lanes per row: global -> shared with cp.async (LDGSTS: no
-    // registers, completion tracked per commit group).  `g` points at the first chunk of the first row; thanks to the
-    // aprons every row is a plain copy.
-    template <int NROWS, int CH, int PITCH_BYTES>
+    // ROWS (a whole number of rounds) rows of CH 16-byte chunks, LPR (power of two) lanes per row: global -> shared
+    // with cp.async (LDGSTS: no registers, completion tracked per commit group).  `g` points at the first chunk of the
+    // first row; thanks to the aprons every row is a plain copy.  Surplus lanes of a row repeat its last chunk (same
+    // bytes to the same place), so there is no divergence; offsets are 32-bit (a level image is < 2 GiB).
+    template <int ROWS, int CH, int PITCH_BYTES>
     static __device__ __forceinline__ void stage_rows(void* region, int lane, const uint8_t* g, int pitch_bytes)
     {
-        constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = (NROWS + RPR - 1) / RPR;
-        const int ch = lane & (LPR - 1), rr = lane / LPR;
-        if (CH < LPR && ch >= CH) return;
+        constexpr int LPR = pow2_at_least(CH), RPR = 32 / LPR, ROUNDS = ROWS / RPR;
+        static_assert(ROWS % RPR == 0, "regions are staged in whole rounds");
+        const int ch = CH < LPR ? min(lane & (LPR - 1), CH - 1) : (lane & (LPR - 1)), rr = lane / LPR;
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(region) + rr * PITCH_BYTES + ch * 16;
-        g += (long long)rr * pitch_bytes + ch * 16;
-        const long long step = (long long)RPR * pitch_bytes;
+        g += rr * pitch_bytes + ch * 16;
+        const long long step = RPR * pitch_bytes;
 #pragma unroll
         for (int i = 0; i < ROUNDS; i++) {
-            if ((i + 1) * RPR > NROWS && rr + i * RPR >= NROWS) break;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * RPR * PITCH_BYTES), "l"(g) : "memory");
             g += step;
         }
@@ -192,8 +201,8 @@ struct Tracker {
                                                    int& rx0, int& ry0)
     {
         rx0 = max(-G::PX, min((inx - G::MX) & ~15, pitch - G::PX - G::J_W));
-        ry0 = max(-G::PY, min(iny - G::MY, h + G::PY - G::J_H));
-        stage_rows<G::J_H, G::J_CH, G::J_PW * 4>(sJ, lane, img + (long long)ry0 * pitch + rx0, pitch);
+        ry0 = max(-G::PY, min(iny - G::MY, h + G::PY - G::J_ROWS));
+        stage_rows<G::J_ROWS, G::J_CH, G::J_PW * 4>(sJ, lane, img + (ry0 * pitch + rx0), pitch);
     }
     // first staged column of the template window / its derivatives for window origin x = ipx
     static __device__ __forceinline__ int x0_I(int ipx, int pitch) { return min(ipx & ~15, pitch - G::PX - G::I_W); }
@@ -202,13 +211,12 @@ struct Tracker {
     // Template window of the previous image: WH+1 rows from ipy, I_W bytes from x0_I
     static __device__ __forceinline__ void stage_I(unsigned* sI, const uint8_t* __restrict__ img, int pitch, int ipx, int ipy, int lane)
     {
-        stage_rows<WH + 1, G::I_CH, G::I_PW * 4>(sI, lane, img + (long long)ipy * pitch + x0_I(ipx, pitch), pitch);
+        stage_rows<G::I_ROWS, G::I_CH, G::I_PW * 4>(sI, lane, img + (ipy * pitch + x0_I(ipx, pitch)), pitch);
     }
     // Scharr derivatives of the template window (the apron holds the zeros outside the image): WH+1 rows, D_CH*4 words
     static __device__ __forceinline__ void stage_D(unsigned* sD, const int* __restrict__ der, int dpitch, int ipx, int ipy, int lane)
     {
-        stage_rows<WH + 1, G::D_CH, G::D_PW * 4>(sD, lane, reinterpret_cast<const uint8_t*>(der + (long long)ipy * dpitch + x0_D(ipx, dpitch)),
-                                                 dpitch * 4);
+        stage_rows<G::D_ROWS, G::D_CH, G::D_PW * 4>(sD, lane, reinterpret_cast<const uint8_t*>(der + (ipy * dpitch + x0_D(ipx, dpitch))), dpitch * 4);
     }
 };
 
@@ -249,23 +257,28 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     const bool want_err = P.err != nullptr;
     const bool get_min_eig = (P.flags & DR3LK_GET_MIN_EIGENVALS) != 0;
 
-    // window origin of the template at `level` for previous-frame point pp; false when it is out of frame
-    auto template_origin = [&](const float2 pp, int level, int& ipx, int& ipy, float& fx, float& fy) -> bool {
-        const float sc = __int_as_float((127 - level) << 23);
-        fx = __fsub_rn(__fmul_rn(pp.x, sc), hwx);
-        fy = __fsub_rn(__fmul_rn(pp.y, sc), hwy);
-        ipx = __float2int_rd(fx); ipy = __float2int_rd(fy);
-        const LevelDesc& L = P.lv[level];
-        return (unsigned)(ipx + WW) < (unsigned)(L.w + WW) && (unsigned)(ipy + WH) < (unsigned)(L.h + WH);
-    };
-    // issue the copies of the template window (image + derivatives) of (pair, pp, level) into sI / sD
-    auto issue_template = [&](int pair, const float2 pp, int level) {
+    // Template window of previous-frame point pp at `level`: origin (ipx, ipy), sub-pixel position (fx, fy), in-frame flag
+    struct Origin {
         int ipx, ipy;
         float fx, fy;
-        if (!template_origin(pp, level, ipx, ipy, fx, fy)) return;
+        bool inb;
+    };
+    auto template_origin = [&](const float2 pp, int level) -> Origin {
+        Origin o;
+        const float sc = __int_as_float((127 - level) << 23);
+        o.fx = __fsub_rn(__fmul_rn(pp.x, sc), hwx);
+        o.fy = __fsub_rn(__fmul_rn(pp.y, sc), hwy);
+        o.ipx = __float2int_rd(o.fx); o.ipy = __float2int_rd(o.fy);
         const LevelDesc& L = P.lv[level];
-        T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, ipx, ipy, lane);
-        T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, ipx, ipy, lane);
+        o.inb = (unsigned)(o.ipx + WW) < (unsigned)(L.w + WW) && (unsigned)(o.ipy + WH) < (unsigned)(L.h + WH);
+        return o;
+    };
+    // issue the copies of the template window (image + derivatives) at origin o of (pair, level) into sI / sD
+    auto issue_template = [&](int pair, const Origin& o, int level) {
+        if (!o.inb) return;
+        const LevelDesc& L = P.lv[level];
+        T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, o.ipx, o.ipy, lane);
+        T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, o.ipx, o.ipy, lane);
     };
     auto fetch = [&]() -> int {
         int f = 0;
@@ -279,7 +292,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     if (f >= P.n_total) return;
     float2 pp = P.prev_pts[f];
     int pair = pair_of(f);
-    issue_template(pair, pp, P.max_level);
+    Origin org = template_origin(pp, P.max_level);  // always the origin of the template window that is in flight / staged
+    issue_template(pair, org, P.max_level);
     cp_async_commit();
 
     for (;;) {
@@ -302,9 +316,9 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             const float sc = __int_as_float((127 - level) << 23);
             const uint8_t* imgJ = L.next + (unsigned long long)(unsigned)pair * L.next_stride;
 
-            int ipx, ipy;
-            float px, py;
-            const bool inb = template_origin(pp, level, ipx, ipy, px, py);
+            const int ipx = org.ipx, ipy = org.ipy;
+            const float px = org.fx, py = org.fy;
+            const bool inb = org.inb;
             float nx, ny;
             if (level == P.max_level) {
                 if (P.flags & DR3LK_USE_INITIAL_FLOW) { nx = __fmul_rn(np.x, sc); ny = __fmul_rn(np.y, sc); }
@@ -315,16 +329,21 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             np.x = nx; np.y = ny;
             nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
 
+            // The staged search region as the iterations see it: window origins (vx0 .. vx0 + vxs, vy0 .. vy0 + vys) are
+            // BOTH inside the staged region and inside the frame (OpenCV's bounds test), so one range test per axis
+            // serves both; jb0 turns an origin into its byte offset in sJ.  Nothing staged: an empty range.
+            int vx0 = 0x40000000, vy0 = 0x40000000, vxs = 0, vys = 0, jb0 = 0;
+            auto stage_search = [&](int ox, int oy) {
+                int rx0, ry0;
+                T::stage_J(sJ, imgJ, L.pitch_n, h, ox, oy, lane, rx0, ry0);
+                vx0 = max(rx0, -WW); vxs = min(rx0 + (G::J_W - (WW + 1)), w - 1) - vx0;
+                vy0 = max(ry0, -WH); vys = min(ry0 + 2 * G::MY, h - 1) - vy0;
+                jb0 = -(ry0 * (G::J_PW * 4) + rx0);
+            };
             // search region around the initial estimate: issued now, consumed after the template phase
-            int rx0 = 0, ry0 = 0;
-            constexpr int vspan = G::J_W - (WW + 1);
-            bool staged = false;
             if (inb) {
                 const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
-                if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) {
-                    T::stage_J(sJ, imgJ, L.pitch_n, h, jx, jy, lane, rx0, ry0);
-                    staged = true;
-                }
+                if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) stage_search(jx, jy);
             }
             cp_async_commit();
             cp_async_wait<1>();  // everything older than the search region: this level's template window has landed
@@ -366,8 +385,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             // the template regions are free again: prefetch the next template window (next finer level of this
             // feature, or the coarsest level of the next feature) behind the iterations
             __syncwarp();
-            if (level > 0) issue_template(pair, pp, level - 1);
-            else if (f_next < P.n_total) issue_template(pair_next, pp_next, P.max_level);
+            if (level > 0) { org = template_origin(pp, level - 1); issue_template(pair, org, level - 1); }
+            else if (f_next < P.n_total) { org = template_origin(pp_next, P.max_level); issue_template(pair_next, org, P.max_level); }
             cp_async_commit();
 
             if (!inb) {
@@ -388,7 +407,9 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 if (level == 0) status = 0;
                 continue;
             }
-            D = __fdiv_rn(1.f, D);
+            // 1/D with the 2^-20 scale of the mismatch vector folded in: scaling by a power of two commutes with every
+            // rounding below (no under/overflow: |b| < 2^35, 2^-23 <= D), so b1, b2 stay unscaled
+            const float Ds = __fmul_rn(__fdiv_rn(1.f, D), FLT_SCALE);
 
             // ---- iterations ----
             cp_async_wait<1>();  // the search region has landed (the template prefetch may still be in flight)
@@ -397,20 +418,20 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             bool moved = false;
             for (int j = 0; j < P.max_count; ++j) {
                 const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-                if ((unsigned)(inx + WW) >= (unsigned)(w + WW) || (unsigned)(iny + WH) >= (unsigned)(h + WH)) {
-                    if (level == 0) status = 0;
-                    break;
-                }
-                q = make_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
-                if (!staged || (unsigned)(inx - rx0) > (unsigned)vspan || (unsigned)(iny - ry0) > (unsigned)(2 * G::MY)) {
+                if ((unsigned)(inx - vx0) > (unsigned)vxs || (unsigned)(iny - vy0) > (unsigned)vys) {
+                    // left the staged search region -- or the frame
+                    if ((unsigned)(inx + WW) >= (unsigned)(w + WW) || (unsigned)(iny + WH) >= (unsigned)(h + WH)) {
+                        if (level == 0) status = 0;
+                        break;
+                    }
                     __syncwarp();
-                    T::stage_J(sJ, imgJ, L.pitch_n, h, inx, iny, lane, rx0, ry0);
+                    stage_search(inx, iny);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncwarp();
-                    staged = true;
                 }
-                const int jbase = (iny - ry0) * (G::J_PW * 4) + (inx - rx0);
+                q = make_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
+                const int jbase = iny * (G::J_PW * 4) + inx + jb0;
                 int b1 = 0, b2 = 0;
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
@@ -425,11 +446,11 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 }
                 const HiLo sb1 = warp_sum_hilo(b1), sb2 = warp_sum_hilo(b2);
                 n_iters++;
-                // exact integer sums, one rounding to fp32
-                const float fb1 = __fmul_rn(hilo_to_float(sb1.hi, sb1.lo), FLT_SCALE);
-                const float fb2 = __fmul_rn(hilo_to_float(sb2.hi, sb2.lo), FLT_SCALE);
-                const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
-                const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+                // exact integer sums, one rounding to fp32 (the 2^-20 scale lives in Ds)
+                const float fb1 = hilo_to_float(sb1.hi, sb1.lo);
+                const float fb2 = hilo_to_float(sb2.hi, sb2.lo);
+                const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), Ds);
+                const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), Ds);
                 nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
                 moved = true;
                 // |delta|^2 <= eps^2 in double like OpenCV; the fp32 estimate decides unless it is within 1e-6 of the threshold
@@ -457,14 +478,14 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     continue;
                 }
                 q = make_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy));
-                if (!staged || (unsigned)(iqx - rx0) > (unsigned)vspan || (unsigned)(iqy - ry0) > (unsigned)(2 * G::MY)) {
+                if ((unsigned)(iqx - vx0) > (unsigned)vxs || (unsigned)(iqy - vy0) > (unsigned)vys) {
                     __syncwarp();
-                    T::stage_J(sJ, imgJ, L.pitch_n, h, iqx, iqy, lane, rx0, ry0);
+                    stage_search(iqx, iqy);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncwarp();
                 }
-                const int jbase = (iqy - ry0) * (G::J_PW * 4) + (iqx - rx0);
+                const int jbase = iqy * (G::J_PW * 4) + iqx + jb0;
                 int es = 0;
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
