@@ -241,6 +241,7 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         a.n_prev = batch; a.n_next = (down && next0) ? batch : 0;
         a.down = down;
         a.dst_apron_x = P.ax; a.dst_apron_y = P.ay;
+        a.src_apron_x = P.ax; a.src_apron_y = P.ay;
         if (down) {
             a.prev_dst = const_cast<uint8_t*>(lk.lv[l + 1].prev); a.next_dst = const_cast<uint8_t*>(lk.lv[l + 1].next);
             a.prev_dst_stride = lk.lv[l + 1].prev_stride; a.next_dst_stride = lk.lv[l + 1].next_stride;
@@ -833,6 +834,7 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
         pa.n_prev = 1; pa.n_next = 0;
         pa.down = l < P.ml;
         pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
+        pa.src_apron_x = P.ax; pa.src_apron_y = P.ay;
         if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
         launch_pyr_level(L, pa);
     }

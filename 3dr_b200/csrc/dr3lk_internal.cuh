@@ -76,6 +76,7 @@ struct PyrLevelArgs {
     int n_prev, n_next;
     bool down;
     int dst_apron_x, dst_apron_y;  // > 0: also write the REFLECT_101 apron of the down-sampled level
+    int src_apron_x, src_apron_y;  // apron the source level carries (0: none -- tiles at the image edge reflect indices)
 };
 void launch_pyr_level(Launch& L, const PyrLevelArgs& a);
 // Level 0 into its apron-carrying scratch copy: dst(x, y) = src(reflect101(x), reflect101(y)) for -ax <= x < w + ax,

@@ -37,7 +37,7 @@ struct PyrSet {
 template <bool DOWN>
 __global__ void __launch_bounds__(PYR_THREADS)
 pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int src_aligned, int dst_pitch, int* __restrict__ deriv,
-                 int dpitch, unsigned deriv_stride, int apron_x, int apron_y)
+                 int dpitch, unsigned deriv_stride, int apron_x, int apron_y, int src_ax, int src_ay)
 {
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
     __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
@@ -55,7 +55,16 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
 
     // columns xs-2 .. xs+2*TOX+1 are needed; the vector path also requires the 16-byte chunks to stay inside the row
     const bool xin = src_aligned && blockIdx.x >= 1 && xs + 2 * TOX + 2 <= w && x0 + SW <= src_pitch;
-    if (xin) {
+    if (src_aligned && src_ax >= HX && src_ay >= 2 && w >= 3 && h >= 3) {  // (the two apron pixels a tile uses are single reflections)
+        // the source level carries its REFLECT_101 apron: every row / column the tile needs is in memory, so every tile is
+        // plain 16-byte row copies (chunks / rows beyond the apron are never read back from the tile)
+        for (int idx = tid; idx < SH * (SW / 16); idx += PYR_THREADS) {
+            const int ty = idx / (SW / 16), ch = idx - ty * (SW / 16);
+            const int sx = x0 + ch * 16, sy = min(y0 + ty, h + src_ay - 1);
+            if (sx + 16 <= src_pitch - src_ax)
+                *reinterpret_cast<uint4*>(&tile[ty][ch * 16]) = __ldg(reinterpret_cast<const uint4*>(s + (long long)sy * src_pitch + sx));
+        }
+    } else if (xin) {
         for (int idx = tid; idx < SH * (SW / 16); idx += PYR_THREADS) {
             const int ty = idx / (SW / 16), ch = idx - ty * (SW / 16);
             const int sy = reflect101(y0 + ty, h);
@@ -175,41 +184,62 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
 
 // Level 0 with its REFLECT_101 apron: one 16-byte destination chunk per thread.  Interior chunks read the source row
 // through aligned 32-bit words realigned with funnel shifts (the caller's rows may have any alignment, e.g. continuous
-// 1241-wide images); apron chunks gather byte-wise through the reflected indices.
-__global__ void __launch_bounds__(128)
+// 1241-wide images).
+constexpr int PAD_TX = 32, PAD_TY = 8, PAD_RPT = 4;  // block = 32 chunk columns x 8 rows, 4 rows per thread
+
+// 16 destination bytes at column x of one row (x is a multiple of 16, -ax <= x): dst[x + i] = srow[reflect101(x + i)].
+// A chunk that lies completely inside the row, or completely in the left / right apron, is 16 CONSECUTIVE source
+// bytes, forwards or backwards: one branch-free path (aligned 32-bit loads, funnel shifts, byte reversal) serves all
+// three, so warps do not diverge.  Only the chunk that straddles the right image edge gathers byte by byte.
+__device__ __forceinline__ uint4 pad_chunk(const uint8_t* __restrict__ srow, int x, int w)
+{
+    // first source byte: x (interior), -(x + 15) (left apron, reversed), 2(w-1) - (x + 15) (right apron, reversed)
+    const bool left = x + 15 < 0 && -x <= w - 1, right = x >= w && 2 * (w - 1) - (x + 15) >= 0;
+    if (left || right || (x >= 0 && x + 16 <= w)) {
+        const int s0 = left ? -(x + 15) : (right ? 2 * (w - 1) - (x + 15) : x);
+        const uint8_t* p = srow + s0;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+        const unsigned* pw = reinterpret_cast<const unsigned*>(p - mis);
+        const unsigned sh = mis * 8;
+        // the fifth word is only touched when the chunk is misaligned: it ends inside the word holding byte s0 + 15
+        const unsigned w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3), w4 = mis ? __ldg(pw + 4) : 0u;
+        const unsigned f0 = __funnelshift_r(w0, w1, sh), f1 = __funnelshift_r(w1, w2, sh), f2 = __funnelshift_r(w2, w3, sh),
+                       f3 = __funnelshift_r(w3, w4, sh);
+        if (!(left || right)) return make_uint4(f0, f1, f2, f3);
+        return make_uint4(__byte_perm(f3, 0, 0x0123), __byte_perm(f2, 0, 0x0123), __byte_perm(f1, 0, 0x0123), __byte_perm(f0, 0, 0x0123));
+    }
+    unsigned o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        o[i >> 2] |= (unsigned)__ldg(srow + reflect101(x + i, w)) << (8 * (i & 3));
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(PAD_TX * PAD_TY)
 pad_level0_kernel(const uint8_t* __restrict__ src_a, const uint8_t* __restrict__ src_b, long long src_pitch, long long src_stride,
                   uint8_t* __restrict__ dst_a, uint8_t* __restrict__ dst_b, int dst_pitch, long long dst_stride, int w, int h, int ax, int ay,
                   int n_a)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * PAD_TX + threadIdx.x;
     if (c * 16 >= dst_pitch) return;
-    const int x = c * 16 - ax, y = (int)blockIdx.y - ay;
+    const int x = c * 16 - ax;
     const bool set_b = (int)blockIdx.z >= n_a;
     const int img = set_b ? blockIdx.z - n_a : blockIdx.z;
-    const uint8_t* srow = (set_b ? src_b : src_a) + (long long)img * src_stride + (long long)reflect101(y, h) * src_pitch;
-    uint8_t* dst = set_b ? dst_b : dst_a;
-    uint4 v;
-    if (x >= 0 && x + 16 <= w) {
-        const uint8_t* p = srow + x;
-        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
-        const unsigned* pw = reinterpret_cast<const unsigned*>(p - mis);
-        const unsigned w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3);
-        if (mis == 0) {
-            v = make_uint4(w0, w1, w2, w3);
-        } else {
-            const unsigned w4 = __ldg(pw + 4), sh = mis * 8;  // the last word ends inside the word holding byte x + 15
-            v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-        }
-    } else {
-        unsigned o[4] = {0, 0, 0, 0};
+    const uint8_t* src = (set_b ? src_b : src_a) + (long long)img * src_stride;
+    uint8_t* dst = (set_b ? dst_b : dst_a) + (long long)img * dst_stride + x;
+    const int r0 = blockIdx.y * (PAD_TY * PAD_RPT) + threadIdx.y;  // row index in the apron-carrying image
+    uint4 v[PAD_RPT];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int xx = x + i;
-            if (xx < w + ax) o[i >> 2] |= (unsigned)__ldg(srow + reflect101(xx, w)) << (8 * (i & 3));
-        }
-        v = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int k = 0; k < PAD_RPT; k++) {
+        const int r = r0 + k * PAD_TY;
+        if (r < h + 2 * ay) v[k] = pad_chunk(src + (long long)reflect101(r - ay, h) * src_pitch, x, w);
     }
-    *reinterpret_cast<uint4*>(dst + (long long)img * dst_stride + (long long)y * dst_pitch + x) = v;
+#pragma unroll
+    for (int k = 0; k < PAD_RPT; k++) {
+        const int r = r0 + k * PAD_TY;
+        if (r < h + 2 * ay) *reinterpret_cast<uint4*>(dst + (long long)(r - ay) * dst_pitch) = v[k];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -246,10 +276,10 @@ void launch_pyr_level(Launch& L, const PyrLevelArgs& a)
     PyrSet B{a.next_src, a.next_dst, a.next_src_stride, a.next_dst_stride};
     if (a.down)
         pyr_level_kernel<true><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                 a.deriv_stride, a.dst_apron_x, a.dst_apron_y);
+                                                                 a.deriv_stride, a.dst_apron_x, a.dst_apron_y, a.src_apron_x, a.src_apron_y);
     else
         pyr_level_kernel<false><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                  a.deriv_stride, 0, 0);
+                                                                  a.deriv_stride, 0, 0, a.src_apron_x, a.src_apron_y);
     L.err = cudaGetLastError();
     L.launches++;
 }
@@ -258,8 +288,8 @@ void launch_pad_level0(Launch& L, const uint8_t* src_a, const uint8_t* src_b, si
                        uint8_t* dst_b, int dst_pitch, size_t dst_stride, int w, int h, int ax, int ay, int n_a, int n_b)
 {
     if (L.err != cudaSuccess || n_a + n_b <= 0) return;
-    dim3 grid((dst_pitch / 16 + 127) / 128, h + 2 * ay, n_a + n_b);
-    pad_level0_kernel<<<grid, 128, 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b, dst_pitch,
+    dim3 grid((dst_pitch / 16 + PAD_TX - 1) / PAD_TX, (h + 2 * ay + PAD_TY * PAD_RPT - 1) / (PAD_TY * PAD_RPT), n_a + n_b);
+    pad_level0_kernel<<<grid, dim3(PAD_TX, PAD_TY), 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b, dst_pitch,
                                                   (long long)dst_stride, w, h, ax, ay, n_a);
     L.err = cudaGetLastError();
     L.launches++;
