@@ -670,19 +670,29 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     for (int i = 0; i < dr3lk_ctx::kSlots; i++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ev_start, 0));
     cudaEventDestroy(ev_start);
 
+    // Chunk boundaries.  chunk_pairs > 0: equal chunks of that many pairs.  0 = choose: ~128 MB of level-0 pixels per
+    // chunk (few launches, short tails), at most the batch split in 2 * kSlots pieces, and a geometric ramp-up from
+    // small first chunks so that the first kernels start after microseconds of H2D instead of a full chunk's copy.
+    std::vector<int> cb;  // chunk c = pairs cb[c] .. cb[c + 1]
+    cb.push_back(0);
     if (chunk_pairs <= 0) {
-        // aim at ~64 MB of level-0 pixels per chunk, at least 1 pair, at most the batch split in kSlots*2 pieces
         const size_t per_pair = 2 * (size_t)w * h;
-        chunk_pairs = (int)std::max<size_t>(1, (64u << 20) / per_pair);
-        chunk_pairs = std::min(chunk_pairs, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
+        int full = (int)std::max<size_t>(1, (128u << 20) / per_pair);
+        full = std::min(full, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
+        int next = std::max(1, full / 16);
+        while (cb.back() < batch) {
+            cb.push_back(std::min(batch, cb.back() + next));
+            next = std::min(full, next * 2);
+        }
+    } else {
+        while (cb.back() < batch) cb.push_back(std::min(batch, cb.back() + chunk_pairs));
     }
-    chunk_pairs = std::min(chunk_pairs, batch);
-    const int n_chunks = (batch + chunk_pairs - 1) / chunk_pairs;
+    const int n_chunks = (int)cb.size() - 1;
     std::vector<int> offs_host;  // all chunks' rebased offsets; must outlive the async copies
     offs_host.reserve((size_t)batch + n_chunks);
     std::vector<size_t> offs_pos(n_chunks);
     for (int c = 0; c < n_chunks; c++) {
-        const int b0 = c * chunk_pairs, b1 = std::min(batch, b0 + chunk_pairs);
+        const int b0 = cb[c], b1 = cb[c + 1];
         offs_pos[c] = offs_host.size();
         for (int b = b0; b <= b1; b++) offs_host.push_back(pts_offset[b] - pts_offset[b0]);
     }
@@ -690,7 +700,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         const int slot = c % dr3lk_ctx::kSlots;
         Workspace& W = ctx->slot_ws[slot];
         cudaStream_t st = ctx->slot_stream[slot];
-        const int b0 = c * chunk_pairs, b1 = std::min(batch, b0 + chunk_pairs), nb = b1 - b0;
+        const int b0 = cb[c], b1 = cb[c + 1], nb = b1 - b0;
         const int p0 = pts_offset[b0], n = pts_offset[b1] - p0;
         if (n == 0) continue;
         // Level-0 pixels cross PCIe as ONE contiguous copy per frame set in the caller's own layout (2-D copies with an
