@@ -87,29 +87,31 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
         for (int ly = tid >> 5; ly < 2 * TOY; ly += PYR_THREADS / 32) {
             const int sx = xs + 4 * g, sy = ys + ly;
             if (sx < w && sy < h) {
-                int t0[6], t1[6];
                 const unsigned* r0 = reinterpret_cast<const unsigned*>(&tile[ly + 1][HX - 4 + 4 * g]);
                 const unsigned* r1 = reinterpret_cast<const unsigned*>(&tile[ly + 2][HX - 4 + 4 * g]);
                 const unsigned* r2 = reinterpret_cast<const unsigned*>(&tile[ly + 3][HX - 4 + 4 * g]);
-                const unsigned a0 = r0[0], a1 = r0[1], a2 = r0[2];
-                const unsigned b0 = r1[0], b1 = r1[1], b2 = r1[2];
-                const unsigned c0 = r2[0], c1 = r2[1], c2 = r2[2];
+                // Bytes 3..8 of the 12 loaded per row are columns sx-1 .. sx+4.  Two columns per register as 16-bit lanes:
+                // P[0] = columns (1,3), P[1] = (4,6), P[2] = (5,7), P[3] = (8,10) -- odd / even bytes of the three words.
+                // All lane values stay in [0, 65535], so plain 32-bit adds / small multiplies act lane-wise.
+                unsigned T0[4], T1[4];
 #pragma unroll
-                for (int i = 0; i < 6; i++) {   // column sx - 1 + i = byte 3 + i of the 12 loaded bytes
-                    const int k = 3 + i;
-                    const int a = (int)byte_of(k < 4 ? a0 : (k < 8 ? a1 : a2), k & 3);
-                    const int b = (int)byte_of(k < 4 ? b0 : (k < 8 ? b1 : b2), k & 3);
-                    const int c = (int)byte_of(k < 4 ? c0 : (k < 8 ? c1 : c2), k & 3);
-                    t0[i] = 3 * (a + c) + 10 * b;   // vertical smooth
-                    t1[i] = c - a;                  // vertical difference
+                for (int i = 0; i < 4; i++) {
+                    const int wi = (i + 1) >> 1;                         // word 0, 1, 1, 2
+                    const unsigned sel = (i == 0 || i == 2) ? 0x4341u : 0x4240u;  // odd bytes (b1, b3) / even bytes (b0, b2)
+                    const unsigned a = __byte_perm(r0[wi], 0, sel), b = __byte_perm(r1[wi], 0, sel), c = __byte_perm(r2[wi], 0, sel);
+                    T0[i] = (a + c) * 3u + b * 10u;          // vertical smooth, <= 4080 per lane
+                    T1[i] = c + 0x08000800u - a;             // vertical difference + 2048 per lane
                 }
+                // horizontal pass; the lanes of ix / iy carry +32768 (removed by the final xor): no borrows between lanes
+                const unsigned ixe = T0[2] + 0x80008000u - __byte_perm(T0[0], T0[2], 0x5432);   // columns 4, 6: (5,7) - (3,5)
+                const unsigned ixo = __byte_perm(T0[1], T0[3], 0x5432) + 0x80008000u - T0[1];   // columns 5, 7: (6,8) - (4,6)
+                const unsigned iye = (__byte_perm(T1[0], T1[2], 0x5432) + T1[2]) * 3u + T1[1] * 10u;
+                const unsigned iyo = (T1[1] + __byte_perm(T1[1], T1[3], 0x5432)) * 3u + T1[2] * 10u;
                 int o[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int ix = t0[j + 2] - t0[j];
-                    const int iy = 3 * (t1[j] + t1[j + 2]) + 10 * t1[j + 1];
-                    o[j] = (ix & 0xffff) | (iy << 16);
-                }
+                o[0] = (int)(__byte_perm(ixe, iye, 0x5410) ^ 0x80008000u);
+                o[1] = (int)(__byte_perm(ixo, iyo, 0x5410) ^ 0x80008000u);
+                o[2] = (int)(__byte_perm(ixe, iye, 0x7632) ^ 0x80008000u);
+                o[3] = (int)(__byte_perm(ixo, iyo, 0x7632) ^ 0x80008000u);
                 int* out = d + (long long)sy * dpitch + sx;
                 if (sx + 3 < w) {
                     *reinterpret_cast<int4*>(out) = make_int4(o[0], o[1], o[2], o[3]);
