@@ -52,7 +52,10 @@ struct Geo {
 #ifndef DR3LK_BLOCKS_SMALL
 #define DR3LK_BLOCKS_SMALL 4
 #endif
-    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? DR3LK_BLOCKS_SMALL : 3;  // measured best: 16 warps/SM at <= 128 registers (21x21), 12 at <= 168 (31x31, 30x30)
+#ifndef DR3LK_BLOCKS_LARGE
+#define DR3LK_BLOCKS_LARGE 3
+#endif
+    static constexpr int MIN_BLOCKS = (NRUN * R <= 16) ? DR3LK_BLOCKS_SMALL : DR3LK_BLOCKS_LARGE;  // measured best: 16 warps/SM at <= 128 registers (21x21), 12 at <= 168 (31x31, 30x30)
     static constexpr int MX = 13, MY = 8;                // search-region margins (x margin is >= MX after alignment)
     static constexpr int J_CH = (WW + 1 + 2 * MX + 15 + 15) / 16;  // 16-B chunks per search-region row
     static constexpr int J_W = J_CH * 16;

@@ -126,5 +126,23 @@ t, tracked, n = device_batch(prev_k, next_k, kp * reps, (21, 21), 3, (3, 30, 0.0
 tc = sum(cpu_time(frames[i], frames[i + 1], kp[i], (21, 21), 3, (3, 30, 0.01), n=3) for i in range(9))
 out["kitti_batch_21x21"] = {"pairs": 9 * reps, "points": n, "tracked_fraction": tracked / n, "gpu_features_per_s": n / t,
                             "gpu_tracked_per_s": tracked / t, "cv2_features_per_s": sum(len(k) for k in kp) / tc}
+# ---- "next" rows of SURVEY.md 8f through their host-buffer C-ABI calls, next to the CPU restatements (oracle/) on the host
+import oracle  # noqa: E402
+from oracle import postfilter  # noqa: E402
+t = time_call(lambda: ctx.fast_detect(frames[0]), n=20)
+tc = time_call(lambda: oracle.fast_detector(frames[0]), n=3, warm=1)
+xy, lv, sc = ctx.fast_detect(frames[0])
+out["f1_fast_detect_kitti0"] = {"corners": int(len(xy)), "gpu_call_ms": 1e3 * t, "cpu_restatement_ms": 1e3 * tc, "cpu": "oracle/fast_oracle.c, 1 thread"}
+p1, s1, _ = ctx.calc_optical_flow_pyr_lk(frames[0], frames[1], pts)
+t = time_call(lambda: ctx.filter_tracks(pts, p1, s1, 718.856, 718.856, 607.19, 185.22), n=20)
+tc = time_call(lambda: postfilter.filter_tracks(pts, p1, s1, 718.856, 718.856, 607.19, 185.22), n=5, warm=1)
+out["f3_filter_tracks"] = {"points": int(len(pts)), "gpu_call_ms": 1e3 * t, "cpu_restatement_ms": 1e3 * tc, "cpu": "oracle/postfilter.py (numpy)"}
+rng = np.random.default_rng(5)
+keep = s1 == 1
+F = rng.normal(0, 1e-3, (200, 3, 3)).astype(np.float32)
+t = time_call(lambda: ctx.score_fundamental(F, pts[keep], p1[keep], 1.0), n=20)
+tc = time_call(lambda: postfilter.check_fundamental(F, pts[keep], p1[keep], 1.0), n=1, warm=0)
+out["f4_score_fundamental"] = {"hypotheses": 200, "matches": int(keep.sum()), "gpu_call_ms": 1e3 * t, "cpu_restatement_ms": 1e3 * tc,
+                               "cpu": "oracle/postfilter.py (numpy across hypotheses, python loop over matches in the reference's fp32 order)"}
 out["host"] = {"cpus": os.cpu_count(), "cv2": cv2_ref.CV2_VERSION, "gpu": torch.cuda.get_device_name(0)}
 print(json.dumps(out, indent=1))
