@@ -35,6 +35,39 @@ UNIT = "features/s"
 WIN, MAX_LEVEL, CRIT, FLAGS = (21, 21), 3, (3, 30, 0.01), 0
 W_IMG, H_IMG, CORNERS = 1241, 376, 8192
 
+# The headline workload is C3 (BASELINE.json configs[2], the one `metric` is quoted on).  --workload runs the other named
+# shapes through exactly the same code (informational; the driver only runs the default):
+#   name: (description, W, H, window, maxLevel, default pairs per GPU, default distinct pairs)
+WORKLOADS = {
+    "c3": ("C3: synthetic 1241x376 frame pairs x 8192 corners, 4-level 21x21 LK (30 it, eps 0.01)", 1241, 376, (21, 21), 3, 4096, 32),
+    "kitti": ("KITTI: the 9 bundled consecutive pairs data/kitti0..9 (1240x376) tiled, cv2 FAST corners of each previous frame, "
+              "4-level 21x21 LK (30 it, eps 0.01)", 1240, 376, (21, 21), 3, 2304, 9),
+    "c4": ("C4: synthetic 3840x2160 frame pairs x 50000 corners, 5-level 31x31 LK (30 it, eps 0.01)", 3840, 2160, (31, 31), 4, 64, 2),
+    "c5": ("C5: semi-dense 4-px lattice (29140 points) on synthetic 1241x376 frame pairs, 4-level 21x21 LK (30 it, eps 0.01)",
+           1241, 376, (21, 21), 3, 1024, 16),
+}
+
+
+def make_workload(name, nb, seed0):
+    """nb distinct frame pairs of the workload: prev (nb,H,W) u8, next, pts (N,2) f32, offsets (nb+1,) i32."""
+    from tools import synth
+    if name == "c3":
+        return synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=seed0)
+    if name == "c5":
+        return synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=seed0, points="lattice")
+    if name == "c4":
+        return synth.make_batch(nb, W_IMG, H_IMG, 50000, seed0=1000 + seed0, min_dist=5)
+    if name == "kitti":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _common import load_gray
+        from oracle import cv2_ref
+        frames = [load_gray("kitti%d.png" % i) for i in range(10)]
+        sel = [i % 9 for i in range(nb)]
+        pts = [cv2_ref.fast_corners(frames[i])[0] for i in sel]
+        offs = np.concatenate([[0], np.cumsum([len(p) for p in pts])]).astype(np.int32)
+        return (np.stack([frames[i] for i in sel]), np.stack([frames[i + 1] for i in sel]), np.concatenate(pts).astype(np.float32), offs)
+    raise SystemExit("unknown workload " + name)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,9 +75,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
-    ap.add_argument("--base-pairs", type=int, default=32, help="distinct synthetic pairs generated per rank")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=512, help="pairs per reference-arm step; the cpu_baseline leg uses 3x")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (0: the workload's default, 4096 for c3)")
+    ap.add_argument("--base-pairs", type=int, default=0, help="distinct pairs generated per rank (0: the workload's default, 32 for c3)")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs per reference-arm step; the cpu_baseline leg uses 3x (0: 512 for c3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -144,8 +178,13 @@ def emit(obj):
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, WIN, MAX_LEVEL, W_IMG, H_IMG, CORNERS
     args = parse()
+    desc, W_IMG, H_IMG, WIN, MAX_LEVEL, d_pairs, d_base = WORKLOADS[args.workload]
+    args.pairs = args.pairs or d_pairs
+    args.base_pairs = args.base_pairs or d_base
+    data_kind = "bundled KITTI frames (data/kitti0..9), tiled" if args.workload == "kitti" else "synthetic"
+    args.cpu_sample_pairs = args.cpu_sample_pairs or {"c3": 512, "kitti": 512, "c5": 128, "c4": 16}[args.workload]
     # libraries (NCCL version banner, torchrun notices) print to fd 1: keep stdout clean for the JSON line
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
@@ -153,7 +192,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg = {"workload": "C3: synthetic 1241x376 frame pairs x 8192 corners, 4-level 21x21 LK (30 it, eps 0.01)",
+    cfg = {"workload": desc,
            "pairs_per_gpu": args.pairs, "corners_per_pair": CORNERS, "distinct_pairs_per_gpu": args.base_pairs,
            "sharding": "independent frame pairs per GPU, no collective", "win": list(WIN), "max_level": MAX_LEVEL}
 
@@ -164,7 +203,9 @@ def main():
         if rank != 0:
             return
         nb = max(1, min(args.base_pairs, args.cpu_sample_pairs))
-        prev, nxt, pts, offs = synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=1000)
+        prev, nxt, pts, offs = make_workload(args.workload, nb, 1000)
+        CORNERS = int(round(len(pts) / nb))
+        cfg["corners_per_pair"] = CORNERS
         idx = np.arange(args.cpu_sample_pairs) % nb
         P, N = prev[idx], nxt[idx]
         lens = np.diff(offs)[idx]
@@ -181,7 +222,7 @@ def main():
         sample = "%d pairs x %d corners per step (bounded sample of the %d-pair workload), %s" % (args.cpu_sample_pairs, CORNERS, args.pairs, r["what"])
         emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "int32 fixed-point + fp32 solve", "data": "synthetic", "config": cfg,
+                          "vs_baseline": None, "dtype": "int32 fixed-point + fp32 solve", "data": data_kind, "config": cfg,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "submitted_features_per_s": tot_f / tot_t}))
@@ -199,12 +240,14 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     nb = max(1, min(args.base_pairs, args.pairs))
-    prev_b, next_b, pts_b, offs_b = synth.make_batch(nb, W_IMG, H_IMG, CORNERS, seed0=1000 + rank * nb)
+    prev_b, next_b, pts_b, offs_b = make_workload(args.workload, nb, 1000 + rank * nb)
     idx = np.arange(args.pairs) % nb
     lens = np.diff(offs_b)[idx]
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     pts = np.concatenate([pts_b[offs_b[i]:offs_b[i + 1]] for i in idx]).astype(np.float32)
     n_feat = int(offs[-1])
+    CORNERS = int(round(n_feat / args.pairs))
+    cfg["corners_per_pair"] = CORNERS
     t_idx = torch.from_numpy(idx).to(dev)
     prev_d = torch.from_numpy(prev_b).to(dev)[t_idx].contiguous()   # (pairs, H, W) distinct device buffers
     next_d = torch.from_numpy(next_b).to(dev)[t_idx].contiguous()
@@ -279,6 +322,8 @@ def main():
     # DRAM traffic of the LK launch: bytes/feature from the committed ncu --set full capture, scaled to this launch
     traffic, traffic_src = None, None
     try:
+        if args.workload != "c3":
+            raise KeyError("the committed capture is of the C3 kernel")
         with open(os.path.join(ROOT, "profiles", "lk_traffic_r01.json")) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_per_feature"] * n_feat
@@ -289,8 +334,8 @@ def main():
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "lk_ms_per_launch": lk_ms_avg, "pyramid_ms_per_step": pyr_ms / max(lk_n, 1),
             "lk_iterations_per_feature": iters_per_feat,
-            "note": "algorithmic bytes = sum over features of (5T*levels_with_template + T*iterations + T*err_pass + 21), T=(21+1)^2 "
-                    "(SURVEY.md 8d); the kernel's working set is L2-resident so DRAM traffic is far below this"}
+            "note": "algorithmic bytes = sum over features of (5T*levels_with_template + T*iterations + T*err_pass + 21), T=(%d+1)^2 "
+                    "(SURVEY.md 8d); the kernel's working set is L2-resident so DRAM traffic is far below this" % WIN[0]}
 
     # ---- end to end through the host-buffer C ABI
     e2e = None
@@ -357,7 +402,7 @@ def main():
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "int32 fixed-point windows + fp32 2x2 solve", "data": "synthetic", "config": dict(cfg, l2="inputs (%.1f GB/GPU/step) larger than L2" % ((2 * args.pairs * W_IMG * H_IMG) / 1e9)),
+               "dtype": "int32 fixed-point windows + fp32 2x2 solve", "data": data_kind, "config": dict(cfg, l2="inputs (%.1f GB/GPU/step) larger than L2" % ((2 * args.pairs * W_IMG * H_IMG) / 1e9)),
                "submitted_features_per_s": feats_all * args.steps / (ms_total * 1e-3), "tracked_fraction": tracked_all / feats_all,
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if e2e:
