@@ -32,7 +32,7 @@ SYMBOLS = [
     "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
-    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
+    "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
     L.dr3lk_pyramid_destroy.restype = None
     L.dr3lk_pyramid_levels.argtypes = [c_void_p]
     L.dr3lk_calc_optical_flow_pyr_lk_cached.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
+    L.dr3lk_track_frame.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail + [c_int, P(c_void_p)]
     L.dr3lk_filter_tracks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, P(c_int)]
     L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
@@ -271,6 +272,32 @@ class Context:
             float(min_eig_threshold)))
         return npts, status, err
 
+    def track_frame(self, prev_pyr, next_img, prev_pts, next_pts=None, max_level=3, criteria=(TERM_COUNT | TERM_EPS, 30, 0.01),
+                    flags=0, min_eig_threshold=1e-4, want_err=True, keep_next=0):
+        """Streaming form: track from a cached previous-frame `Pyramid` into a NEW host image in one call (one upload, the
+        new frame's pyramid, LK, one download).  keep_next: 0 discard the new frame's pyramid, 1 keep its Gaussian levels,
+        2 keep it with derivatives (it can be the previous frame of the next call).  Returns (next_pts, status, err, Pyramid|None)."""
+        img1 = _gray(next_img)
+        if img1.shape != prev_pyr.shape:
+            raise Dr3lkError(E_SIZE, "(-215:Assertion failed) prevImg.size() == nextImg.size()")
+        pp = np.ascontiguousarray(np.asarray(prev_pts, np.float32).reshape(-1, 2))
+        n = pp.shape[0]
+        if flags & USE_INITIAL_FLOW:
+            npts = np.ascontiguousarray(np.asarray(next_pts, np.float32).reshape(-1, 2)).copy()
+            if npts.shape[0] != n:
+                raise Dr3lkError(E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints")
+        else:
+            npts = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32) if want_err else None
+        win = prev_pyr.win
+        out = ctypes.c_void_p()
+        self._check(lib().dr3lk_track_frame(
+            self._h, prev_pyr._h, img1.ctypes.data, img1.strides[0], pp.ctypes.data, npts.ctypes.data, status.ctypes.data,
+            err.ctypes.data if want_err else None, n, win[0], win[1], max_level, criteria[0], criteria[1], float(criteria[2]), flags,
+            float(min_eig_threshold), keep_next, ctypes.byref(out) if keep_next else None))
+        return npts, status, err, (Pyramid._wrap(self, out, win, prev_pyr.shape) if keep_next else None)
+
     def filter_tracks(self, ref_pts, cur_pts, status, fx=None, fy=None, cx=0.0, cy=0.0):
         """Reference src/initialization.cpp:615-635: drop status == 0 (order kept), disparity norms and, when a pinhole
         (fx, fy, cx, cy) is given, unit bearing vectors of the current points. Returns (ref, cur, disparity, bearing|None)."""
@@ -370,6 +397,13 @@ class Pyramid:
         self.ctx, self.win, self.shape = ctx, tuple(win), (h, w)
         ctx._check(lib().dr3lk_pyramid_create(ctx._h, img0.ctypes.data, w, h, img0.strides[0], win[0], win[1], max_level,
                                               ctypes.byref(self._h)))
+
+    @classmethod
+    def _wrap(cls, ctx, handle, win, shape):
+        """Adopt a pyramid handle returned by the library (Context.track_frame)."""
+        self = cls.__new__(cls)
+        self._h, self.ctx, self.win, self.shape = handle, ctx, tuple(win), tuple(shape)
+        return self
 
     @property
     def levels(self):

@@ -318,6 +318,8 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
                        uint8_t* status_dev, float* err_dev, const int* pts_offset, const int* pts_offset_dev, int n_total,
                        uint32_t* stats_dev, const LKArgs& a)
 {
+    // the pyramid kernels put the image index (both frames of every pair) in gridDim.z
+    if (batch > 32767) return fail(ctx, DR3LK_E_SIZE, "at most 32767 frame pairs per device-resident call: split the batch");
     LKParams lk;
     memset(&lk, 0, sizeof(lk));
     PyrLayout P = make_layout(w, h, a.win_w, a.win_h, a.max_level);
@@ -782,8 +784,90 @@ struct dr3lk_pyramid {
     int w, h, win_w, win_h;
     PyrLayout P;
     DevBuf img, deriv;
+    bool has_deriv = true;     // false: Gaussian levels only (usable as the `next` side of a call only)
+    size_t der_total = 0;      // ints in `deriv`
     LevelDesc lv[kMaxLevels];  // prev / deriv fields describe this frame
 };
+
+// Allocates the device buffers of a pyramid object (from the context's pool when possible) and fills its level
+// descriptors.  with_deriv = false: Gaussian levels only (a frame that is only ever the `next` side of a call).
+static int pyramid_alloc(dr3lk_ctx* ctx, int w, int h, int win_w, int win_h, int max_level, bool with_deriv, dr3lk_pyramid** out)
+{
+    dr3lk_pyramid* p = new (std::nothrow) dr3lk_pyramid();
+    if (!p) return fail(ctx, DR3LK_E_CUDA, "out of host memory");
+    p->ctx = ctx; p->w = w; p->h = h; p->win_w = win_w; p->win_h = win_h; p->has_deriv = with_deriv;
+    p->P = make_layout(w, h, win_w, win_h, max_level);
+    const PyrLayout& P = p->P;
+    if (P.img_bytes[0] >= (1ull << 31) || P.der_ints[0] >= (1ull << 29)) { delete p; return fail(ctx, DR3LK_E_SIZE, "images of 2 GiB or more (derivatives included) are not supported"); }
+    size_t img_total = 0, der_total = 0, ioff[kMaxLevels], doff[kMaxLevels];
+    for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
+    p->der_total = der_total;
+    p->img = ctx->take(img_total);
+    cudaError_t e = p->img.reserve(img_total);
+    if (e == cudaSuccess && with_deriv) {
+        p->deriv = ctx->take(der_total * sizeof(int));
+        e = p->deriv.reserve(der_total * sizeof(int));
+    }
+    if (e != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, e, "pyramid: allocation"); }
+    for (int l = 0; l <= P.ml; l++) {
+        LevelDesc& d = p->lv[l];
+        d.w = P.w[l]; d.h = P.h[l];
+        d.prev = d.next = (const uint8_t*)p->img.p + ioff[l] + P.img_org[l];
+        d.pitch_p = d.pitch_n = P.pitch[l];
+        d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
+        d.deriv = with_deriv ? (const int*)p->deriv.p + doff[l] + P.der_org[l] : nullptr;
+        d.dpitch = P.dpitch[l];
+        d.deriv_stride = (unsigned)P.der_ints[l];
+    }
+    *out = p;
+    return DR3LK_OK;
+}
+
+// Enqueues the build of a pyramid object from a level-0 image that is already on the device (16-B pitched scratch,
+// pitch0 = align16(w)): apron copy (or plain copy for windows without aprons), Gaussian levels, derivatives.  No sync.
+static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_dev, cudaStream_t st, Launch& L)
+{
+    const PyrLayout& P = p->P;
+    const int pitch0 = align_up(p->w, 16);
+    const size_t l0_bytes = (size_t)pitch0 * p->h;
+    if (L.err != cudaSuccess) return;
+    if (P.ax > 0) {
+        // level 0 is copied into its apron-carrying image; the derivative aprons are zeros
+        if (p->has_deriv) L.err = cudaMemsetAsync(p->deriv.p, 0, p->der_total * sizeof(int), st);
+        launch_pad_level0(L, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
+                          p->h, P.ax, P.ay, 1, 0);
+    } else {
+        L.err = cudaMemcpyAsync(p->img.p, l0_dev, l0_bytes, cudaMemcpyDeviceToDevice, st);  // P.pitch[0] == pitch0 without aprons
+    }
+    for (int l = 0; l <= P.ml; l++) {
+        const LevelDesc& s = p->lv[l];
+        PyrLevelArgs pa{};
+        pa.prev_src = s.prev; pa.prev_src_stride = s.prev_stride;
+        pa.w = s.w; pa.h = s.h; pa.src_pitch = s.pitch_p;
+        pa.deriv = const_cast<int*>(s.deriv); pa.dpitch = s.dpitch; pa.deriv_stride = s.deriv_stride;
+        pa.n_prev = 1; pa.n_next = 0;
+        pa.down = l < P.ml;
+        if (!pa.down && !pa.deriv) break;  // nothing to produce from the last level
+        pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
+        pa.src_apron_x = P.ax; pa.src_apron_y = P.ay;
+        if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
+        launch_pyr_level(L, pa);
+    }
+    ctx->launches += L.launches;
+    L.launches = 0;
+}
+
+static void pyramid_free(dr3lk_pyramid* p, bool to_pool)
+{
+    dr3lk_ctx* ctx = p->ctx;
+    if (to_pool && ctx->pool.size() < 16) {
+        if (p->img.p) ctx->pool.push_back(p->img);
+        if (p->deriv.p) ctx->pool.push_back(p->deriv);
+    } else {
+        p->img.release(); p->deriv.release();
+    }
+    delete p;
+}
 
 int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h, int max_level,
                          dr3lk_pyramid** out)
@@ -796,62 +880,22 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     if (!img || step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "pyramid_create: bad image arguments");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
-    dr3lk_pyramid* p = new (std::nothrow) dr3lk_pyramid();
-    if (!p) return fail(ctx, DR3LK_E_CUDA, "out of host memory");
-    p->ctx = ctx; p->w = w; p->h = h; p->win_w = win_w; p->win_h = win_h;
-    p->P = make_layout(w, h, win_w, win_h, max_level);
-    const PyrLayout& P = p->P;
-    if (P.img_bytes[0] >= (1ull << 31) || P.der_ints[0] >= (1ull << 29)) { delete p; return fail(ctx, DR3LK_E_SIZE, "images of 2 GiB or more (derivatives included) are not supported"); }
-    size_t img_total = 0, der_total = 0, ioff[kMaxLevels], doff[kMaxLevels];
-    for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
-    p->img = ctx->take(img_total);
-    p->deriv = ctx->take(der_total * sizeof(int));
+    dr3lk_pyramid* p = nullptr;
+    rc = pyramid_alloc(ctx, w, h, win_w, win_h, max_level, true, &p);
+    if (rc != DR3LK_OK) return rc;
     const int pitch0 = align_up(w, 16);
     const size_t l0_bytes = (size_t)pitch0 * h;
-    cudaError_t e = p->img.reserve(img_total);
-    if (e == cudaSuccess) e = p->deriv.reserve(der_total * sizeof(int));
-    if (e == cudaSuccess) e = ctx->pinned.reserve(l0_bytes);
-    if (e == cudaSuccess && P.ax > 0) e = ctx->ws.lvl0_prev.reserve(l0_bytes);
-    if (e != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, e, "pyramid_create: allocation"); }
+    cudaError_t e = ctx->pinned.reserve(l0_bytes);
+    if (e == cudaSuccess) e = ctx->ws.lvl0_prev.reserve(l0_bytes);
+    if (e != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, e, "pyramid_create: allocation"); }
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
-    for (int l = 0; l <= P.ml; l++) {
-        LevelDesc& d = p->lv[l];
-        d.w = P.w[l]; d.h = P.h[l];
-        d.prev = d.next = (const uint8_t*)p->img.p + ioff[l] + P.img_org[l];
-        d.pitch_p = d.pitch_n = P.pitch[l];
-        d.prev_stride = d.next_stride = (unsigned)P.img_bytes[l];
-        d.deriv = (const int*)p->deriv.p + doff[l] + P.der_org[l];
-        d.dpitch = P.dpitch[l];
-        d.deriv_stride = (unsigned)P.der_ints[l];
-    }
     Launch L{st, cudaSuccess, 0};
-    if (P.ax > 0) {
-        // level 0 lands in scratch and is copied into its apron-carrying image; the derivative aprons are zeros
-        L.err = cudaMemcpyAsync(ctx->ws.lvl0_prev.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);
-        if (L.err == cudaSuccess) L.err = cudaMemsetAsync(p->deriv.p, 0, der_total * sizeof(int), st);
-        launch_pad_level0(L, (const uint8_t*)ctx->ws.lvl0_prev.p, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr,
-                          P.pitch[0], P.img_bytes[0], w, h, P.ax, P.ay, 1, 0);
-    } else {
-        L.err = cudaMemcpyAsync(p->img.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);  // P.pitch[0] == pitch0 without aprons
-    }
-    for (int l = 0; l <= P.ml; l++) {
-        const LevelDesc& s = p->lv[l];
-        PyrLevelArgs pa{};
-        pa.prev_src = s.prev; pa.prev_src_stride = s.prev_stride;
-        pa.w = s.w; pa.h = s.h; pa.src_pitch = s.pitch_p;
-        pa.deriv = const_cast<int*>(s.deriv); pa.dpitch = s.dpitch; pa.deriv_stride = s.deriv_stride;
-        pa.n_prev = 1; pa.n_next = 0;
-        pa.down = l < P.ml;
-        pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
-        pa.src_apron_x = P.ax; pa.src_apron_y = P.ay;
-        if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
-        launch_pyr_level(L, pa);
-    }
-    ctx->launches += L.launches;
+    L.err = cudaMemcpyAsync(ctx->ws.lvl0_prev.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);
+    pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, st, L);
     // the pinned staging buffer is reused by the next call: wait for the upload
     if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st);
-    if (L.err != cudaSuccess) { p->img.release(); p->deriv.release(); delete p; return fail_cuda(ctx, L.err, "pyramid_create"); }
+    if (L.err != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, L.err, "pyramid_create"); }
     *out = p;
     return DR3LK_OK;
 }
@@ -861,9 +905,7 @@ void dr3lk_pyramid_destroy(dr3lk_pyramid* pyr)
     if (!pyr) return;
     cudaSetDevice(pyr->ctx->device);
     // stream-ordered reuse is safe: every consumer of these buffers was enqueued on the context's stream before this point
-    if (pyr->ctx->pool.size() < 16) { pyr->ctx->pool.push_back(pyr->img); pyr->ctx->pool.push_back(pyr->deriv); }
-    else { pyr->img.release(); pyr->deriv.release(); }
-    delete pyr;
+    pyramid_free(pyr, true);
 }
 
 int dr3lk_pyramid_levels(const dr3lk_pyramid* pyr) { return pyr ? pyr->P.ml + 1 : 0; }
@@ -881,6 +923,7 @@ int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* p
         return fail(ctx, DR3LK_E_SIZE, "(-215:Assertion failed) prevPyr[level * lvlStep1].size() == nextPyr[level * lvlStep2].size()");
     if (prev->win_w != win_w || prev->win_h != win_h || next->win_w != win_w || next->win_h != win_h)
         return fail(ctx, DR3LK_E_ARG, "pyramids were built for another window size");
+    if (!prev->has_deriv) return fail(ctx, DR3LK_E_ARG, "the previous-frame pyramid was built without derivatives");
     if (n < 0) return fail(ctx, DR3LK_E_ARG, "negative point count");
     if (n == 0) return DR3LK_OK;
     if (!prev_pts || !next_pts || !status) return fail(ctx, DR3LK_E_ARG, "null point / status buffer");
@@ -919,6 +962,84 @@ int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* p
     memcpy(next_pts, hp + o_next, 8 * (size_t)n);
     memcpy(status, hp + o_status, (size_t)n);
     if (err) memcpy(err, hp + o_err, 4 * (size_t)n);
+    return DR3LK_OK;
+}
+
+int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* next_img, size_t next_step, const float* prev_pts,
+                      float* next_pts, uint8_t* status, float* err, int n, int win_w, int win_h, int max_level, int crit_type,
+                      int crit_max_count, double crit_eps, int flags, double min_eig_threshold, int keep_next, dr3lk_pyramid** next_out)
+{
+    if (!ctx || !prev) return DR3LK_E_ARG;
+    if (next_out) *next_out = nullptr;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    const int w = prev->w, h = prev->h;
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (prev->ctx != ctx) return fail(ctx, DR3LK_E_ARG, "the pyramid belongs to another context");
+    if (prev->win_w != win_w || prev->win_h != win_h) return fail(ctx, DR3LK_E_ARG, "the pyramid was built for another window size");
+    if (!prev->has_deriv) return fail(ctx, DR3LK_E_ARG, "the previous-frame pyramid was built without derivatives");
+    if (!next_img || next_step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "track_frame: bad image arguments");
+    if (keep_next < 0 || keep_next > 2 || (keep_next && !next_out)) return fail(ctx, DR3LK_E_ARG, "track_frame: keep_next must be 0..2 and needs next_out");
+    if (n < 0) return fail(ctx, DR3LK_E_ARG, "negative point count");
+    if (n > 0 && (!prev_pts || !next_pts || !status)) return fail(ctx, DR3LK_E_ARG, "null point / status buffer");
+    if (n == 0 && !keep_next) return DR3LK_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    dr3lk_pyramid* p2 = nullptr;
+    rc = pyramid_alloc(ctx, w, h, win_w, win_h, max_level, keep_next == 2, &p2);
+    if (rc != DR3LK_OK) return rc;
+    // One device block and one pinned mirror of it: [new image][prev_pts 8n][offsets 16][next_pts 8n][err 4n][status n]:
+    // the image and the points cross PCIe as ONE copy, the results come back as ONE copy, the call synchronises once.
+    const int pitch0 = align_up(w, 16);
+    const size_t img_block = align_up_sz((size_t)pitch0 * h, 256);
+    const size_t n8 = align_up_sz(8 * (size_t)n, 16);
+    const size_t o_prev = img_block, o_offs = o_prev + n8, o_next = o_offs + 16, o_err = o_next + n8, o_status = o_err + align_up_sz(4 * (size_t)n, 16);
+    const size_t total = o_status + align_up_sz((size_t)n, 16);
+    cudaError_t e = W.lvl0_prev.reserve(total);
+    if (e == cudaSuccess) e = ctx->pinned.reserve(total);
+    if (e != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame: allocation"); }
+    uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, next_img + (size_t)y * next_step, (size_t)w);
+    const int offs[2] = {0, n};
+    size_t in_bytes = img_block;
+    if (n > 0) {
+        memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
+        memcpy(hp + o_offs, offs, sizeof(offs));
+        in_bytes = o_next;
+        if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
+    }
+    Launch L{st, cudaSuccess, 0};
+    L.err = cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st);
+    pyramid_enqueue(ctx, p2, dp, st, L);
+    if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
+    if (n > 0) {
+        LKParams lk;
+        memset(&lk, 0, sizeof(lk));
+        const int ml = std::min(std::min(prev->P.ml, p2->P.ml), max_level);
+        for (int l = 0; l <= ml; l++) {
+            lk.lv[l] = prev->lv[l];
+            lk.lv[l].next = p2->lv[l].prev;
+            lk.lv[l].pitch_n = p2->lv[l].pitch_p;
+            lk.lv[l].next_stride = p2->lv[l].prev_stride;
+        }
+        lk.max_level = ml;
+        lk.fast_ok = prev->P.ax > 0;
+        rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status,
+                          err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
+        if (rc != DR3LK_OK) { cudaStreamSynchronize(st); pyramid_free(p2, false); return rc; }
+        e = cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { cudaStreamSynchronize(st); pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame: D2H"); }
+    }
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame"); }
+    if (n > 0) {
+        memcpy(next_pts, hp + o_next, 8 * (size_t)n);
+        memcpy(status, hp + o_status, (size_t)n);
+        if (err) memcpy(err, hp + o_err, 4 * (size_t)n);
+    }
+    if (keep_next) *next_out = p2; else pyramid_free(p2, true);
     return DR3LK_OK;
 }
 

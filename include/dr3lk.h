@@ -138,6 +138,17 @@ int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* p
                                           int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
                                           double min_eig_threshold);
 
+/* Streaming form of the same row, for the per-frame loop of the reference (src/handler.cpp:31-48: one new image per call,
+ * tracked against a frame that is already on the device -- the anchored reference frame of Init::process_second_frame or
+ * simply the previous frame of a chain).  ONE call = one H2D copy (new image + points), the new frame's pyramid, LK, one
+ * D2H copy, one synchronisation; results are identical to dr3lk_calc_optical_flow_pyr_lk on the two source images.
+ * keep_next: 0 = discard the new frame's pyramid; 1 = return it in *next_out with Gaussian levels only (it can be the
+ * `next` side of later calls); 2 = return it with derivatives (it is the `prev` of the following call). */
+int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* next_img, size_t next_step,
+                      const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n, int win_w, int win_h,
+                      int max_level, int crit_type, int crit_max_count, double crit_eps, int flags, double min_eig_threshold,
+                      int keep_next, dr3lk_pyramid** next_out);
+
 /* f-3: the step right after the LK call, reference src/initialization.cpp:615-635 -- drop the points with status == 0
  * (order preserved, like the erase loop), disparity = ||ref - cur|| (double), and the unit bearing vector of the current
  * point for an undistorted pinhole camera ((u-cx)/fx, (v-cy)/fy, 1) normalised (src/camera.cpp:25-41, !_distortion).

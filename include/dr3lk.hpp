@@ -152,6 +152,8 @@ public:
     {
         ctx_->check(dr3lk_pyramid_create(ctx_->get(), img.data, img.cols, img.rows, img.step, winSize.width, winSize.height, maxLevel, &pyr_));
     }
+    // adopts a pyramid returned by the library (trackFrame)
+    Pyramid(Context& context, dr3lk_pyramid* pyr, Size winSize) : ctx_(&context), pyr_(pyr), win_(winSize) {}
     ~Pyramid() { dr3lk_pyramid_destroy(pyr_); }
     Pyramid(const Pyramid&) = delete;
     Pyramid& operator=(const Pyramid&) = delete;
@@ -189,6 +191,34 @@ inline void calcOpticalFlowPyrLK(const Pyramid& prevPyr, const Pyramid& nextPyr,
                                                   reinterpret_cast<float*>(nextPts.data()), status.data(), err.data(), static_cast<int>(n),
                                                   win.width, win.height, maxLevel, criteria.type, criteria.maxCount, criteria.epsilon, flags,
                                                   minEigThreshold));
+}
+
+// Streaming form for the per-frame loop (src/handler.cpp:31-48): track from a frame that is already on the device into a
+// NEW image in one call (one upload, the new frame's pyramid, LK, one download).  keepNext: 0 discard the new frame's
+// pyramid, 1 keep its Gaussian levels, 2 keep it with derivatives (the previous frame of the next call).
+template <class P2f>
+inline std::unique_ptr<Pyramid> trackFrame(const Pyramid& prevPyr, const Image& nextImg, const std::vector<P2f>& prevPts,
+                                           std::vector<P2f>& nextPts, std::vector<unsigned char>& status, std::vector<float>& err,
+                                           int maxLevel = 3, TermCriteria criteria = TermCriteria(TermCriteria::COUNT + TermCriteria::EPS, 30, 0.01),
+                                           int flags = 0, double minEigThreshold = 1e-4, int keepNext = 2)
+{
+    static_assert(sizeof(P2f) == 2 * sizeof(float), "points must be two packed floats (x, y)");
+    Context& c = prevPyr.context();
+    const size_t n = prevPts.size();
+    if (flags & OPTFLOW_USE_INITIAL_FLOW) {
+        if (nextPts.size() != n) throw Exception(DR3LK_E_ARG, "(-215:Assertion failed) nextPtsMat.checkVector(2, CV_32F, true) == npoints");
+    } else {
+        nextPts.resize(n);
+    }
+    status.resize(n);
+    err.resize(n);
+    const Size win = prevPyr.winSize();
+    dr3lk_pyramid* out = nullptr;
+    c.check(dr3lk_track_frame(c.get(), prevPyr.get(), nextImg.data, nextImg.step, reinterpret_cast<const float*>(prevPts.data()),
+                              reinterpret_cast<float*>(nextPts.data()), status.data(), err.data(), static_cast<int>(n), win.width, win.height,
+                              maxLevel, criteria.type, criteria.maxCount, criteria.epsilon, flags, minEigThreshold, keepNext,
+                              keepNext ? &out : nullptr));
+    return std::unique_ptr<Pyramid>(out ? new Pyramid(c, out, win) : nullptr);
 }
 
 // ---- the erase-by-status loop of src/initialization.cpp:615-635 in one call ----

@@ -38,6 +38,50 @@ def test_cached_pyramids_give_identical_results(ctx, dr3):
         p.close()
 
 
+def test_track_frame_streaming_matches_plain_calls(ctx, dr3):
+    """dr3lk_track_frame: one call per new frame against a frame that is already on the device -- a frame-to-frame chain
+    (keep_next=2), the reference's anchored warm-start loop (keep_next=0 / 1) and the 30x30 window; bit-identical to the
+    plain two-image call and to the oracle."""
+    frames = [load_gray("kitti%d.png" % i) for i in range(5)]
+    pts = golden_case("c1_default_21x21")["prev_pts"][:1500]
+    prev = dr3.Pyramid(ctx, frames[0], (21, 21), 3)
+    cur = pts
+    for i in range(4):
+        p, s, e, nxt = ctx.track_frame(prev, frames[i + 1], cur, keep_next=2)
+        orc = oracle.calc_optical_flow_pyr_lk(frames[i], frames[i + 1], cur)
+        for a, c in zip((p, s, e), orc):
+            assert np.array_equal(a.view(np.uint8), c.view(np.uint8)), i
+        assert nxt.levels == 4
+        prev.close()
+        prev, cur = nxt, p[s == 1]
+    prev.close()
+    # anchored: the reference frame stays, every new frame is tracked with a warm start (src/initialization.cpp:608-613)
+    anchor = dr3.Pyramid(ctx, frames[0], (30, 30), 4)
+    ref, curp = pts.copy(), pts.copy()
+    for i in (1, 2, 3):
+        p, s, e, keep = ctx.track_frame(anchor, frames[i], ref, curp, 4, (3, 1000, 1e-3), dr3.USE_INITIAL_FLOW, keep_next=i % 2)
+        orc = oracle.calc_optical_flow_pyr_lk(frames[0], frames[i], ref, curp, (30, 30), 4, (3, 1000, 1e-3), dr3.USE_INITIAL_FLOW)
+        for a, c in zip((p, s, e), orc):
+            assert np.array_equal(a.view(np.uint8), c.view(np.uint8)), i
+        if keep is not None:
+            # a Gaussian-only pyramid can be the next side again, but not the previous side
+            q = ctx.calc_optical_flow_pyr_lk_cached(anchor, keep, ref, curp, 4, (3, 1000, 1e-3), dr3.USE_INITIAL_FLOW)
+            assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(q, orc))
+            with pytest.raises(dr3.Dr3lkError):
+                ctx.calc_optical_flow_pyr_lk_cached(keep, anchor, ref)
+            keep.close()
+        ref, curp = ref[s == 1], p[s == 1]
+    # no points: the new frame's pyramid is still built when asked for
+    p, s, e, nxt = ctx.track_frame(anchor, frames[4], np.zeros((0, 2), np.float32), keep_next=2)
+    assert p.shape == (0, 2) and nxt is not None and nxt.levels == 4
+    q = ctx.calc_optical_flow_pyr_lk_cached(nxt, anchor, pts)
+    orc = oracle.calc_optical_flow_pyr_lk(frames[4], frames[0], pts, None, (30, 30), 4)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(q, orc))
+    with pytest.raises(dr3.Dr3lkError):
+        ctx.track_frame(anchor, frames[1][:, :-8], pts)
+    nxt.close(); anchor.close()
+
+
 def test_filter_tracks_matches_restatement(ctx):
     rng = np.random.default_rng(12)
     for n in (1, 7, 1023, 1024, 1025, 4607, 20000):

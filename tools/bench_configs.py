@@ -78,6 +78,23 @@ def chain_cached():
 
 t_cached = time_call(chain_cached, n=10)
 out["c2_chain_cached_pyramids_ms"] = 1e3 * t_cached
+
+
+def chain_streaming():
+    # one call per incoming frame: upload + pyramid of the new frame + LK against the previous frame's cached pyramid
+    prev_pyr = dr3.Pyramid(ctx, frames[0], (21, 21), 3)
+    cur, surv = pts, []
+    for i in range(9):
+        p, s, _, nxt_pyr = ctx.track_frame(prev_pyr, frames[i + 1], cur, keep_next=2)
+        cur = p[s == 1]; surv.append(len(cur))
+        prev_pyr.close()
+        prev_pyr = nxt_pyr
+    prev_pyr.close()
+    return surv
+
+
+out["c2_chain_streaming_ms"] = 1e3 * time_call(chain_streaming, n=10)
+assert chain_streaming() == chain_cached()
 out["c2_chain"] = {"survivors": chain(lambda x, y, c: ctx.calc_optical_flow_pyr_lk(x, y, c)), "gpu_chain_ms": 1e3 * t, "cv2_chain_ms": 1e3 * tc}
 
 
