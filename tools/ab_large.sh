@@ -1,4 +1,7 @@
-for rep in 1 2; do for t in l3 l4; do
+#!/bin/bash
+# usage (under gpurun): tools/ab_large.sh tagA tagB ...  -- A/B of library variants (tools/ab_build.sh) on the configs that
+# use the 31x31 / 30x30 kernels (C4, the reference's literal parameters) plus the single-call latencies
+for rep in 1 2; do for t in "$@"; do
 DR3LK_LIB=$PWD/3dr_b200/lib/libdr3lk_$t.so python tools/bench_configs.py 2>/dev/null | python -c "
 import json,sys
 d=json.load(sys.stdin)
