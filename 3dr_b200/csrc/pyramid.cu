@@ -130,11 +130,13 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
         for (int ty = tid >> 5; ty < SH; ty += PYR_THREADS / 32) {
             const unsigned* r = reinterpret_cast<const unsigned*>(&tile[ty][HX - 4 + 4 * m]);
             const unsigned w0 = r[0], w1 = r[1], w2 = r[2];
-            const int b2 = byte_of(w0, 2), b3 = byte_of(w0, 3), b4 = byte_of(w1, 0), b5 = byte_of(w1, 1), b6 = byte_of(w1, 2),
-                      b7 = byte_of(w1, 3), b8 = byte_of(w2, 0);
-            const int h0 = b2 + 4 * b3 + 6 * b4 + 4 * b5 + b6;
-            const int h1 = b4 + 4 * b5 + 6 * b6 + 4 * b7 + b8;
-            *reinterpret_cast<short2*>(&hrow[ty][2 * m]) = make_short2((short)h0, (short)h1);
+            // two outputs per register on 16-bit lanes (values <= 16 * 255): bytes b2..b8 of the three words, even bytes
+            // E = (b0, b2), odd bytes O = (b1, b3) of a word; (hi of one, lo of the next) pairs come from one PRMT
+            const unsigned e0 = __byte_perm(w0, 0, 0x4240), o0 = __byte_perm(w0, 0, 0x4341), e1 = __byte_perm(w1, 0, 0x4240),
+                           o1 = __byte_perm(w1, 0, 0x4341), e2 = __byte_perm(w2, 0, 0x4240);
+            const unsigned p24 = __byte_perm(e0, e1, 0x5432), p35 = __byte_perm(o0, o1, 0x5432), p68 = __byte_perm(e1, e2, 0x5432);
+            // (h0, h1) = (b2, b4) + 4 (b3, b5) + 6 (b4, b6) + 4 (b5, b7) + (b6, b8)
+            *reinterpret_cast<unsigned*>(&hrow[ty][2 * m]) = (p24 + p68) + (p35 + o1) * 4u + e1 * 6u;
         }
         __syncthreads();
         const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
@@ -142,13 +144,19 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
         const int q = tid & 15, oy = tid >> 4;   // 4 outputs per thread, 16 threads per row, 16 rows
         const int gx = blockIdx.x * TOX + 4 * q, gy = blockIdx.y * TOY + oy;
         if (gx < dw && gy < dh) {
-            int v[4] = {128, 128, 128, 128};
+            // vertical [1 4 6 4 1] on the same 16-bit lanes: 128 + 16 * 4080 < 65536, so (sum + 128) >> 8 is the high byte
+            // of each lane and one PRMT packs the four output pixels
+            unsigned v01 = 0x00800080u, v23 = 0x00800080u;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
-                const short4 hv = *reinterpret_cast<const short4*>(&hrow[2 * oy + k][4 * q]);
-                const int c = (k == 0 || k == 4) ? 1 : (k == 2 ? 6 : 4);
-                v[0] += c * hv.x; v[1] += c * hv.y; v[2] += c * hv.z; v[3] += c * hv.w;
+                const uint2 hv = *reinterpret_cast<const uint2*>(&hrow[2 * oy + k][4 * q]);
+                const unsigned c = (k == 0 || k == 4) ? 1u : (k == 2 ? 6u : 4u);
+                v01 += c * hv.x; v23 += c * hv.y;
             }
+            const unsigned word = __byte_perm(v01, v23, 0x7531);
+            unsigned v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = ((word >> (8 * j)) & 0xffu) << 8;  // kept in the old "v >> 8" form for the stores below
             // the row itself plus its REFLECT_101 images in the apron rows (row g mirrors to -g and to 2(dh-1)-g)
             int ys[3] = {gy, gy, gy};
             int ny = 1;
@@ -163,8 +171,7 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
                 uint8_t* row = o + (long long)ys[i] * dst_pitch;
                 uint8_t* out = row + gx;
                 if (gx + 3 < dw && (dst_pitch & 3) == 0) {
-                    *reinterpret_cast<unsigned*>(out) = (unsigned)(v[0] >> 8) | ((unsigned)(v[1] >> 8) << 8) | ((unsigned)(v[2] >> 8) << 16) |
-                                                        ((unsigned)(v[3] >> 8) << 24);
+                    *reinterpret_cast<unsigned*>(out) = word;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
