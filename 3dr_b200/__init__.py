@@ -90,7 +90,8 @@ def lib():
     L.dr3lk_pyramid_destroy.restype = None
     L.dr3lk_pyramid_levels.argtypes = [c_void_p]
     L.dr3lk_calc_optical_flow_pyr_lk_cached.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
-    L.dr3lk_track_frame.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail + [c_int, P(c_void_p)]
+    if hasattr(L, "dr3lk_track_frame"):  # absent only in older builds loaded through DR3LK_LIB for A/B runs
+        L.dr3lk_track_frame.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail + [c_int, P(c_void_p)]
     L.dr3lk_filter_tracks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, P(c_int)]
     L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,

@@ -346,14 +346,18 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 vy0 = max(ry0, -WH); vys = min(ry0 + 2 * G::MY, h - 1) - vy0;
                 jb0 = -(ry0 * (G::J_PW * 4) + rx0);
             };
+            // Copy discipline: at most ONE cp.async group is in flight whenever the warp waits, and every wait is a
+            // wait_group 0.  (An earlier version kept the template prefetch and the search region in flight together and
+            // relied on wait_group 1 retiring them in issue order; under back-to-back levels -- zero iterations -- that
+            // let a template phase start on a window that had not landed, about once in 10^5 features.)
+            cp_async_wait<0>();  // this level's template window (prefetched during the previous level) has landed
+            __syncwarp();
             // search region around the initial estimate: issued now, consumed after the template phase
             if (inb) {
                 const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
                 if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) stage_search(jx, jy);
             }
             cp_async_commit();
-            cp_async_wait<1>();  // everything older than the search region: this level's template window has landed
-            __syncwarp();
 
             int dxr[NRUN][R], dyr[NRUN][R];
             int jinit[NRUN][R];  // 2^8 - 512 * I: the dp2a addend that turns the J sample into (J - I)
@@ -388,7 +392,9 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     }
                 }
             }
-            // the template regions are free again: prefetch the next template window (next finer level of this
+            // the search region has landed behind the template phase ...
+            cp_async_wait<0>();
+            // ... and the template regions are free again: prefetch the next template window (next finer level of this
             // feature, or the coarsest level of the next feature) behind the iterations
             __syncwarp();
             if (level > 0) { org = template_origin(pp, level - 1); issue_template(pair, org, level - 1); }
@@ -417,9 +423,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             // rounding below (no under/overflow: |b| < 2^35, 2^-23 <= D), so b1, b2 stay unscaled
             const float Ds = __fmul_rn(__fdiv_rn(1.f, D), FLT_SCALE);
 
-            // ---- iterations ----
-            cp_async_wait<1>();  // the search region has landed (the template prefetch may still be in flight)
-            __syncwarp();
+            // ---- iterations (the search region landed above; only the template prefetch is in flight) ----
             float pdx = 0.f, pdy = 0.f;
             bool moved = false;
             // The realigned source bytes of the search window stay in registers across iterations (G::CACHE_J): after

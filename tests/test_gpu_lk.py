@@ -50,6 +50,21 @@ def test_lk_parameter_sweep_bit_exact(ctx, win, ml, crit, flags):
     _assert_bit_exact(got, exp, (win, ml, crit, flags))
 
 
+def test_lk_zero_iterations_repeatable(ctx):
+    """maxCount = 0 runs the levels of a feature back to back (template, no iterations, next template ...), the tightest
+    schedule the asynchronous staging of the kernel sees: every repetition must reproduce the oracle bit for bit.
+    (A kernel that waited on two copy groups in flight with wait_group 1 returned a wrong err for ~1 feature in 10^5 here.)"""
+    a, b = load_gray("kitti3.png"), load_gray("kitti4.png")
+    pts = random_points(np.random.default_rng(2103), a.shape[1], a.shape[0], 1500)
+    pts[::7] = np.round(pts[::7])
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, (21, 21), 3, (3, 0, 0.01), 0)
+    for rep in range(400):
+        _assert_bit_exact(ctx.calc_optical_flow_pyr_lk(a, b, pts, None, (21, 21), 3, (3, 0, 0.01), 0), exp, ("rep", rep))
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, (31, 31), 4, (3, 0, 0.01), 0)
+    for rep in range(100):
+        _assert_bit_exact(ctx.calc_optical_flow_pyr_lk(a, b, pts, None, (31, 31), 4, (3, 0, 0.01), 0), exp, ("rep31", rep))
+
+
 def test_lk_without_err_output(ctx):
     a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
     pts = random_points(np.random.default_rng(2), 1240, 376, 800)
