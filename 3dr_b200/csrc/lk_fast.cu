@@ -397,8 +397,12 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             // ... and the template regions are free again: prefetch the next template window (next finer level of this
             // feature, or the coarsest level of the next feature) behind the iterations
             __syncwarp();
-            if (level > 0) { org = template_origin(pp, level - 1); issue_template(pair, org, level - 1); }
-            else if (f_next < P.n_total) { org = template_origin(pp_next, P.max_level); issue_template(pair_next, org, P.max_level); }
+            if (level > 0 || f_next < P.n_total) {  // one copy of the staging code serves both cases
+                const float2 pq = level > 0 ? pp : pp_next;
+                const int pair_q = level > 0 ? pair : pair_next, level_q = level > 0 ? level - 1 : P.max_level;
+                org = template_origin(pq, level_q);
+                issue_template(pair_q, org, level_q);
+            }
             cp_async_commit();
 
             if (!inb) {
