@@ -293,6 +293,24 @@ def main():
         step_device(stats=True)
     torch.cuda.synchronize()
     tracked_per_step = int(st_d.sum().item())
+
+    def replicas_consistent():
+        """Size-independent self-check at full scale: the batch tiles `nb` distinct pairs, so every copy of a pair must
+        produce bit-identical positions, status, err and iteration counts wherever it sits in the batch."""
+        first = {}
+        for b in range(args.pairs):
+            first.setdefault(int(idx[b]), b)
+        ok = True
+        for b in range(args.pairs):
+            r = first[int(idx[b])]
+            if r == b:
+                continue
+            a0, a1, r0, r1 = int(offs[b]), int(offs[b + 1]), int(offs[r]), int(offs[r + 1])
+            ok = ok and bool(torch.equal(nxt_d[a0:a1].view(torch.int32), nxt_d[r0:r1].view(torch.int32)) and torch.equal(st_d[a0:a1], st_d[r0:r1])
+                             and torch.equal(err_d[a0:a1].view(torch.int32), err_d[r0:r1].view(torch.int32)) and torch.equal(stats_d[a0:a1], stats_d[r0:r1]))
+        return ok
+
+    replicas_ok = replicas_consistent()
     stats_h = stats_d.cpu().numpy().view(np.uint32)
     alg_bytes = dr3.algorithmic_bytes(stats_h, WIN)
     iters_per_feat = float(dr3.decode_stats(stats_h)[0].mean())
@@ -404,7 +422,8 @@ def main():
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "int32 fixed-point windows + fp32 2x2 solve", "data": data_kind, "config": dict(cfg, l2="inputs (%.1f GB/GPU/step) larger than L2" % ((2 * args.pairs * W_IMG * H_IMG) / 1e9)),
                "submitted_features_per_s": feats_all * args.steps / (ms_total * 1e-3), "tracked_fraction": tracked_all / feats_all,
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+               "replicas_consistent": replicas_ok}
         if e2e:
             out["e2e"] = e2e
         if cpu:
