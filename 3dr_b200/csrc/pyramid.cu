@@ -251,26 +251,71 @@ pad_level0_kernel(const uint8_t* __restrict__ src_a, const uint8_t* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(256)
+// 16 consecutive bytes at any alignment through aligned 32-bit loads and funnel shifts (the 5th word is only touched
+// when the address is misaligned: it then holds byte 15, so every load stays inside words that hold requested bytes)
+__device__ __forceinline__ void load16(const uint8_t* __restrict__ p, unsigned (&o)[4])
+{
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+    const unsigned* pw = reinterpret_cast<const unsigned*>(p - mis);
+    const unsigned sh = mis * 8;
+    const unsigned w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3), w4 = mis ? __ldg(pw + 4) : 0u;
+    o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+}
+
+// utils::reduce_to_half (src/utils.cpp:382-419).  The scalar walk advances `top` by 2 per pixel and by `stride` per row
+// (lines 410-417), so output row i starts at flat offset i*(2*out_w + stride): for even widths the plain 2x2 box, for odd
+// widths the one-byte-per-row shear of the reference.  Eight outputs per thread: 16 + 16 source bytes at any alignment,
+// two outputs per register on 16-bit lanes (even / odd source bytes), both rounding modes; the ragged end of a row
+// falls back to one output at a time.
+__global__ void __launch_bounds__(128)
 box_half_kernel(const uint8_t* __restrict__ src, int out_w, int out_h, long long row_stride, long long src_img_stride,
                 uint8_t* __restrict__ dst, long long dst_img_stride, int sse2_rounding)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= out_w || i >= out_h) return;
-    const uint8_t* s = src + (long long)blockIdx.z * src_img_stride;
-    // reduce_to_half's scalar walk: `top` advances 2 per pixel and `stride` per row (src/utils.cpp:410-417), so
-    // output row i starts at flat offset i*(2*out_w + stride); for even widths this is the plain 2x2 box.
-    const long long t = (long long)i * (2LL * out_w + row_stride) + 2 * j;
-    const unsigned a = __ldg(s + t), b = __ldg(s + t + 1), c = __ldg(s + t + row_stride), d = __ldg(s + t + row_stride + 1);
-    unsigned v;
-    if (sse2_rounding) {
-        const unsigned v0 = (a + c + 1u) >> 1, v1 = (b + d + 1u) >> 1;  // _mm_avg_epu8 then _mm_avg_epu16
-        v = (v0 + v1 + 1u) >> 1;
+    const int ngroups = (out_w + 7) / 8;                       // groups of 8 outputs per row
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // (row, group) flattened: no idle threads at row ends
+    const int i = idx / ngroups, g = idx - i * ngroups;
+    if (i >= out_h) return;
+    const uint8_t* s = src + (long long)blockIdx.y * src_img_stride + (long long)i * (2LL * out_w + row_stride) + 16 * g;
+    uint8_t* d = dst + (long long)blockIdx.y * dst_img_stride + (long long)i * out_w + 8 * g;
+    if (8 * g + 8 <= out_w) {
+        unsigned t[4], b[4], o[4];
+        load16(s, t);
+        load16(s + row_stride, b);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // word k: source bytes 4k .. 4k+3 of both rows -> outputs 2k, 2k+1 (lanes)
+            const unsigned te = t[k] & 0x00ff00ffu, to = (t[k] >> 8) & 0x00ff00ffu, be = b[k] & 0x00ff00ffu, bo = (b[k] >> 8) & 0x00ff00ffu;
+            if (sse2_rounding) {  // _mm_avg_epu8(top, bottom) then the average of the even / odd bytes, both rounding up
+                const unsigned v0 = ((te + be + 0x00010001u) >> 1) & 0x00ff00ffu, v1 = ((to + bo + 0x00010001u) >> 1) & 0x00ff00ffu;
+                o[k] = ((v0 + v1 + 0x00010001u) >> 1) & 0x00ff00ffu;
+            } else {
+                o[k] = ((te + to + be + bo) >> 2) & 0x00ff00ffu;
+            }
+        }
+        const unsigned w0 = __byte_perm(o[0], o[1], 0x6420), w1 = __byte_perm(o[2], o[3], 0x6420);
+        const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(d) & 3);
+        if (al == 0) {
+            reinterpret_cast<unsigned*>(d)[0] = w0; reinterpret_cast<unsigned*>(d)[1] = w1;
+        } else if (al == 2) {
+            reinterpret_cast<unsigned short*>(d)[0] = (unsigned short)w0;
+            *reinterpret_cast<unsigned*>(d + 2) = __funnelshift_r(w0, w1, 16);
+            reinterpret_cast<unsigned short*>(d)[3] = (unsigned short)(w1 >> 16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { d[k] = (uint8_t)(w0 >> (8 * k)); d[4 + k] = (uint8_t)(w1 >> (8 * k)); }
+        }
     } else {
-        v = (a + b + c + d) >> 2;
+        for (int k = 0; 8 * g + k < out_w; k++) {
+            const unsigned a = __ldg(s + 2 * k), bb = __ldg(s + 2 * k + 1), c = __ldg(s + 2 * k + row_stride), dd = __ldg(s + 2 * k + row_stride + 1);
+            unsigned v;
+            if (sse2_rounding) {
+                const unsigned v0 = (a + c + 1u) >> 1, v1 = (bb + dd + 1u) >> 1;
+                v = (v0 + v1 + 1u) >> 1;
+            } else {
+                v = (a + bb + c + dd) >> 2;
+            }
+            d[k] = (uint8_t)v;
+        }
     }
-    dst[(long long)blockIdx.z * dst_img_stride + (long long)i * out_w + j] = (uint8_t)v;
 }
 
 }  // namespace
@@ -309,8 +354,8 @@ void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_
 {
     if (L.err != cudaSuccess || n_img <= 0) return;
     const int out_w = w / 2, out_h = h / 2;
-    dim3 grid((out_w + 255) / 256, out_h, n_img);
-    box_half_kernel<<<grid, 256, 0, L.stream>>>(src, out_w, out_h, row_stride, src_img_stride, dst, dst_img_stride,
+    dim3 grid((unsigned)(((long long)((out_w + 7) / 8) * out_h + 127) / 128), n_img);
+    box_half_kernel<<<grid, 128, 0, L.stream>>>(src, out_w, out_h, row_stride, src_img_stride, dst, dst_img_stride,
                                                 sse2_rounding);
     L.err = cudaGetLastError();
     L.launches++;

@@ -143,6 +143,34 @@ t, tracked, n = device_batch(prev_k, next_k, kp * reps, (21, 21), 3, (3, 30, 0.0
 tc = sum(cpu_time(frames[i], frames[i + 1], kp[i], (21, 21), 3, (3, 30, 0.01), n=3) for i in range(9))
 out["kitti_batch_21x21"] = {"pairs": 9 * reps, "points": n, "tracked_fraction": tracked / n, "gpu_features_per_s": n / t,
                             "gpu_tracked_per_s": tracked / t, "cv2_features_per_s": sum(len(k) for k in kp) / tc}
+# ---- a-1..a-3: the Frame box pyramid (utils::create_img_pyramid, 3 levels) on device-resident batches
+def box_batch(img, n_img=1024, reps=5):
+    h, w = img.shape
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d0 = torch.from_numpy(np.ascontiguousarray(img)).cuda().unsqueeze(0).repeat(n_img, 1, 1).contiguous()
+        d1 = torch.empty((n_img, h // 2, w // 2), dtype=torch.uint8, device="cuda")
+        d2 = torch.empty((n_img, h // 4, w // 4), dtype=torch.uint8, device="cuda")
+        ctx.set_stream(st.cuda_stream)
+        run = lambda: ctx.box_pyramid_device(d0.data_ptr(), w, h, w, w * h, n_img, [d1.data_ptr(), d2.data_ptr()])
+        run(); st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            run()
+        e1.record(st); st.synchronize()
+        ctx.set_stream(None)
+    t = e0.elapsed_time(e1) / reps * 1e-3
+    nbytes = n_img * (w * h + 2 * (w // 2) * (h // 2) + (w // 4) * (h // 4))  # read L0, write+read L1, write L2
+    tc = time_call(lambda: oracle.box_pyramid(img, 3), n=20)
+    return {"images": n_img, "gpu_us_per_image": 1e6 * t / n_img, "gpu_gb_per_s": nbytes / t / 1e9, "cpu_restatement_us_per_image": 1e6 * tc,
+            "cpu": "oracle/lk_oracle.c (1 thread)"}
+
+
+import oracle  # noqa: E402
+out["a1_box_pyramid_1240x376"] = box_batch(frames[0])
+out["a1_box_pyramid_1241x376_sheared"] = box_batch(load_gray("kitti_000000.png"))
+
 # ---- "next" rows of SURVEY.md 8f through their host-buffer C-ABI calls, next to the CPU restatements (oracle/) on the host
 import oracle  # noqa: E402
 from oracle import postfilter  # noqa: E402
