@@ -50,53 +50,58 @@ filter_tracks_kernel(const float2* __restrict__ ref, const float2* __restrict__ 
     }
 }
 
-// InitHelper::CheckFundamental (src/initialization.cpp:171-249) for many hypotheses.  One thread per
-// hypothesis walks the matches in order, so the fp32 score is accumulated exactly like the reference's scalar loop; the
-// matches are staged through shared memory in tiles so all hypotheses of a block read them once.
-__global__ void __launch_bounds__(128)
+// InitHelper::CheckFundamental (src/initialization.cpp:171-249) for many hypotheses.  One CTA per
+// hypothesis.  The two symmetric-transfer terms of every match (the expensive part: two fp32 divisions) are computed by
+// all threads in parallel into shared memory, a chunk of matches at a time; one thread then adds the chunk's terms to
+// the score strictly in match order, so the fp32 score is accumulated exactly like the reference's scalar loop.  A term
+// the reference skips (chi > th) is stored as +0.0f: x + 0 == x bit for bit (terms that count are >= 2.15, never -0),
+// and a NaN chi is not "> th", so it propagates exactly as in the reference.
+constexpr int SF_THREADS = 128, SF_CHUNK = 1024;
+
+__global__ void __launch_bounds__(SF_THREADS)
 score_fundamental_kernel(const float* __restrict__ F, int n_hyp, const float2* __restrict__ p1, const float2* __restrict__ p2, int n,
                          float inv_sigma2, float* __restrict__ scores, uint8_t* __restrict__ inliers)
 {
-    __shared__ float4 tile[256];
-    const int hyp = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = hyp < n_hyp;
-    float f11 = 0, f12 = 0, f13 = 0, f21 = 0, f22 = 0, f23 = 0, f31 = 0, f32 = 0, f33 = 0;
-    if (active) {
-        const float* f = F + 9 * hyp;
-        f11 = f[0]; f12 = f[1]; f13 = f[2]; f21 = f[3]; f22 = f[4]; f23 = f[5]; f31 = f[6]; f32 = f[7]; f33 = f[8];
-    }
+    __shared__ __align__(16) float2 terms[SF_CHUNK];
+    const int hyp = blockIdx.x;
+    const float* f = F + 9 * hyp;
+    const float f11 = f[0], f12 = f[1], f13 = f[2], f21 = f[3], f22 = f[4], f23 = f[5], f31 = f[6], f32 = f[7], f33 = f[8];
     const float th = 3.841f, thScore = 5.991f;
     float score = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 256) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 256 && i0 + i < n; i += blockDim.x) {
+    for (int i0 = 0; i0 < n; i0 += SF_CHUNK) {
+        const int m = min(SF_CHUNK, n - i0);
+        for (int i = threadIdx.x; i < m; i += SF_THREADS) {
             const float2 a = p1[i0 + i], b = p2[i0 + i];
-            tile[i] = make_float4(a.x, a.y, b.x, b.y);
-        }
-        __syncthreads();
-        if (!active) continue;
-        const int m = min(256, n - i0);
-        for (int i = 0; i < m; i++) {
-            const float u1 = tile[i].x, v1 = tile[i].y, u2 = tile[i].z, v2 = tile[i].w;
-            bool in = true;
+            const float u1 = a.x, v1 = a.y, u2 = b.x, v2 = b.y;
             const float a2 = __fadd_rn(__fadd_rn(__fmul_rn(f11, u1), __fmul_rn(f12, v1)), f13);
             const float b2 = __fadd_rn(__fadd_rn(__fmul_rn(f21, u1), __fmul_rn(f22, v1)), f23);
             const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(f31, u1), __fmul_rn(f32, v1)), f33);
             const float num2 = __fadd_rn(__fadd_rn(__fmul_rn(a2, u2), __fmul_rn(b2, v2)), c2);
             const float sq1 = __fdiv_rn(__fmul_rn(num2, num2), __fadd_rn(__fmul_rn(a2, a2), __fmul_rn(b2, b2)));
             const float chi1 = __fmul_rn(sq1, inv_sigma2);
-            if (chi1 > th) in = false; else score = __fadd_rn(score, __fsub_rn(thScore, chi1));
             const float a1 = __fadd_rn(__fadd_rn(__fmul_rn(f11, u2), __fmul_rn(f21, v2)), f31);
             const float b1 = __fadd_rn(__fadd_rn(__fmul_rn(f12, u2), __fmul_rn(f22, v2)), f32);
             const float c1 = __fadd_rn(__fadd_rn(__fmul_rn(f13, u2), __fmul_rn(f23, v2)), f33);
             const float num1 = __fadd_rn(__fadd_rn(__fmul_rn(a1, u1), __fmul_rn(b1, v1)), c1);
             const float sq2 = __fdiv_rn(__fmul_rn(num1, num1), __fadd_rn(__fmul_rn(a1, a1), __fmul_rn(b1, b1)));
             const float chi2 = __fmul_rn(sq2, inv_sigma2);
-            if (chi2 > th) in = false; else score = __fadd_rn(score, __fsub_rn(thScore, chi2));
-            if (inliers) inliers[(size_t)hyp * n + i0 + i] = in ? 1 : 0;
+            const bool out1 = chi1 > th, out2 = chi2 > th;
+            terms[i] = make_float2(out1 ? 0.f : __fsub_rn(thScore, chi1), out2 ? 0.f : __fsub_rn(thScore, chi2));
+            if (inliers) inliers[(size_t)hyp * n + i0 + i] = (out1 || out2) ? 0 : 1;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float4* t4 = reinterpret_cast<const float4*>(terms);
+            int i = 0;
+            for (; i + 2 <= m; i += 2) {  // two matches (four terms) per 16-byte load, added in match order
+                const float4 t = t4[i >> 1];
+                score = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(score, t.x), t.y), t.z), t.w);
+            }
+            if (i < m) score = __fadd_rn(__fadd_rn(score, terms[i].x), terms[i].y);
+        }
+        __syncthreads();
     }
-    if (active) scores[hyp] = score;
+    if (threadIdx.x == 0) scores[hyp] = score;
 }
 
 }  // namespace
@@ -105,7 +110,7 @@ void launch_score_fundamental(Launch& L, const float* F, int n_hyp, const float*
                               float* scores, uint8_t* inliers)
 {
     if (L.err != cudaSuccess || n_hyp <= 0) return;
-    score_fundamental_kernel<<<(n_hyp + 127) / 128, 128, 0, L.stream>>>(F, n_hyp, (const float2*)p1, (const float2*)p2, n, inv_sigma2,
+    score_fundamental_kernel<<<n_hyp, SF_THREADS, 0, L.stream>>>(F, n_hyp, (const float2*)p1, (const float2*)p2, n, inv_sigma2,
                                                                        scores, inliers);
     L.err = cudaGetLastError();
     L.launches++;
