@@ -45,6 +45,7 @@ struct LKParams {
     int fast_ok;           // every level is 16-B aligned (origin, pitch, stride) and carries the aprons (kApronX, apron_y, deriv_apron_x)
     int* work_counter;     // two device ints (zero-initialised): counter [work_epoch & 1] feeds the persistent warps of
     int work_epoch;        // this launch, which also re-zeroes the other one for the next launch (no memset per call)
+    int fetch_n;           // features a warp reserves per atomic (set by the launcher)
     float eps2_lo, eps2_hi; // fp32 brackets of eps2: below lo / above hi the fp32 estimate of |delta|^2 decides
     double eps2;           // criteria.epsilon^2
     double min_eig_thr;

@@ -18,6 +18,7 @@
 //     results do not depend on summation order.
 //   * Scalar fp32 steps use explicitly rounded intrinsics (no FMA contraction) and match the CPU oracle bit for bit.
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -286,10 +287,16 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, o.ipx, o.ipy, lane);
         T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, o.ipx, o.ipy, lane);
     };
+    // Work distribution: every warp reserves P.fetch_n consecutive features with one atomic (1 for small batches, where
+    // every resident warp should get its own feature; up to 8 for large ones: fewer atomics on the one counter)
+    int f_have = 0, f_end = 0;  // indices f_have .. f_end - 1 are already reserved for this warp
     auto fetch = [&]() -> int {
+        if (f_have < f_end) return f_have++;
         int f = 0;
-        if (lane == 0) f = atomicAdd(P.work_counter + (P.work_epoch & 1), 1);
-        return __shfl_sync(0xffffffffu, f, 0);
+        if (lane == 0) f = atomicAdd(P.work_counter + (P.work_epoch & 1), P.fetch_n);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        f_have = f + 1; f_end = f + P.fetch_n;
+        return f;
     };
     auto pair_of = [&](int f) -> int { return P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f); };
 
@@ -564,7 +571,11 @@ bool launch_one(Launch& L, const LKParams& p)
     if (L.err != cudaSuccess) return false;
     const int want = (p.n_total + G::WARPS - 1) / G::WARPS;
     const int blocks = std::min(want, std::max(1, per_sm) * sms);
-    lk_fast_kernel<G><<<blocks, G::WARPS * 32, smem, L.stream>>>(p);
+    LKParams q = p;
+    static const int fetch_max = getenv("DR3LK_FETCH_MAX") ? atoi(getenv("DR3LK_FETCH_MAX")) : 8;
+    // reserve several features per atomic only when every warp has at least 64 features to work through
+    q.fetch_n = std::max(1, std::min(fetch_max, (int)(p.n_total / (64LL * blocks * G::WARPS))));
+    lk_fast_kernel<G><<<blocks, G::WARPS * 32, smem, L.stream>>>(q);
     L.err = cudaGetLastError();
     L.launches++;
     return L.err == cudaSuccess;  // true: the persistent kernel ran and consumed its work counter
