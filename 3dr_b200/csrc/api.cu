@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -679,7 +680,8 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     cb.push_back(0);
     if (chunk_pairs <= 0) {
         const size_t per_pair = 2 * (size_t)w * h;
-        int full = (int)std::max<size_t>(1, (128u << 20) / per_pair);
+        static const size_t chunk_mb = getenv("DR3LK_CHUNK_MB") ? (size_t)atoi(getenv("DR3LK_CHUNK_MB")) : 128;  // tuning knob
+        int full = (int)std::max<size_t>(1, (chunk_mb << 20) / per_pair);
         full = std::min(full, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
         int next = std::max(1, full / 16);
         while (cb.back() < batch) {
