@@ -263,7 +263,7 @@ void fill_lk_scalars(LKParams& lk, const LKArgs& a)
     lk.eps2 = eps * eps;
     lk.eps2_lo = std::nextafterf((float)(lk.eps2 * (1.0 - 1e-6)), 0.f);
     lk.eps2_hi = std::nextafterf((float)(lk.eps2 * (1.0 + 1e-6)), INFINITY);
-    lk.min_eig_thr = a.min_eig_threshold;
+    lk.min_eig_thr = (float)a.min_eig_threshold;
     lk.win_w = a.win_w; lk.win_h = a.win_h;
     lk.flags = a.flags;
 }

@@ -48,7 +48,7 @@ struct LKParams {
     int fetch_n;           // features a warp reserves per atomic (set by the launcher)
     float eps2_lo, eps2_hi; // fp32 brackets of eps2: below lo / above hi the fp32 estimate of |delta|^2 decides
     double eps2;           // criteria.epsilon^2
-    double min_eig_thr;
+    float min_eig_thr;     // OpenCV's LKTrackerInvoker keeps minEigThreshold as a float: float < float
     int batch;
     int n_total;
     int max_level;         // effective

@@ -158,7 +158,7 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
         const float rad = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
         const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * P.win_w * P.win_h));
         if (want_err && get_min_eig) err = minEig;
-        if ((double)minEig < P.min_eig_thr || D < FLT_EPSILON) {
+        if (minEig < P.min_eig_thr || D < FLT_EPSILON) {
             if (level == 0) status = 0;
             continue;
         }

@@ -17,8 +17,10 @@
  *                    pyramids.cpp: pyrDown) is restated here from SURVEY.md Appendix A.
  *
  * Pinning: the restatement is checked against opencv-python-headless 4.13.0 (`cv2`, the same C++
- * code path the reference calls) by tests/test_oracle_vs_cv2.py when cv2 is importable, and against
+ * code path the reference calls) by tests/test_oracle.py when cv2 is importable, and against
  * the committed fixtures tests/golden/ (generated from cv2 by tests/golden/make_golden.py) otherwise.
+ * The box pyramid is pinned to the reference itself: oracle/_ref (src/utils.cpp:282-430 compiled unmodified by
+ * oracle/build_ref.sh) == this file bit for bit on every shape tests/test_oracle_vs_ref.py tries.
  * Pyramids and Scharr derivatives are bit-exact vs cv2; LK positions agree to a few 1e-3 px because
  * x86 OpenCV accumulates the 2x2 system in fp32 SIMD lanes while this file accumulates the same
  * integer products exactly (int64) and converts once (the GPU does exactly the same, so GPU == oracle
@@ -333,7 +335,8 @@ static void track_point(const orc_level* P, const orc_level* N, int max_level, i
         float D = A11 * A22 - A12 * A12;
         float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win_w * win_h);
         if (err && (flags & ORC_GET_MIN_EIGENVALS)) err[k] = minEig;
-        if ((double)minEig < min_eig_thr || D < FLT_EPSILON) {
+        /* LKTrackerInvoker keeps minEigThreshold as a float member: the test is float < float */
+        if (minEig < (float)min_eig_thr || D < FLT_EPSILON) {
             if (level == 0) status[k] = 0;
             if (tr) { tr->code[k * 32 + level] = 2; tr->pos[(k * 32 + level) * 2] = nx; tr->pos[(k * 32 + level) * 2 + 1] = ny; }
             continue;

@@ -67,6 +67,21 @@ def main():
                             init=ini if ini is not None else np.zeros((0, 2), np.float32), next_pts=p1, status=st, err=err)
         print(case, "n", len(allp), "tracked", int(st.sum()))
 
+    # cv::undistortPoints as Pinhole::cam2world calls it for a distorted camera (src/camera.cpp:32-40): float K / D, 32FC2 points
+    cams = [(458.654, 457.296, 367.215, 248.375, (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0), 752, 480),
+            (718.856, 718.856, 607.1928, 185.2157, (-0.3, 0.1, 0.001, -0.002, 0.05), 1241, 376),
+            (300.0, 300.0, 320.0, 240.0, (0.9, 2.5, 0.01, 0.01, 1.0), 640, 480)]  # the last one reaches the icdist < 0 exit
+    und = {}
+    for ci, (fx, fy, cx, cy, dist, w, h) in enumerate(cams):
+        uv = np.stack([rng.uniform(-100, w + 100, 2000), rng.uniform(-100, h + 100, 2000)], 1).astype(np.float32)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        D = np.array([dist], np.float32)
+        und["cam%d" % ci] = np.array([fx, fy, cx, cy] + list(dist), np.float64)
+        und["uv%d" % ci] = uv
+        und["xy%d" % ci] = cv2.undistortPoints(uv.reshape(-1, 1, 2), K, D).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "undistort.npz"), **und)
+    print("undistort", {k: v.shape for k, v in und.items()})
+
     # frame-to-frame chain kitti0..9 (config C2): survivors per step with default parameters
     frames = [load("kitti%d.png" % i) for i in range(10)]
     pts, _ = cv2_ref.fast_corners(frames[0])

@@ -99,6 +99,24 @@ def test_oracle_vs_cv2_live_pyramids_and_edge_semantics():
         assert m["status_agree"] == 1.0 and m["frac_within_0p01"] >= 0.99, (crit, m)
 
 
+def test_undistort_points_vs_cv2_golden():
+    """oracle/postfilter.undistort_points (the distorted branch of Pinhole::cam2world, src/camera.cpp:32-40) against
+    cv2.undistortPoints outputs frozen by tests/golden/make_golden.py -- bit-exact -- and live when cv2 is importable"""
+    import os
+    from oracle import postfilter
+    from _common import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "undistort.npz"))
+    for ci in range(3):
+        cam, uv, xy = z["cam%d" % ci], z["uv%d" % ci], z["xy%d" % ci]
+        o = postfilter.undistort_points(uv, cam[0], cam[1], cam[2], cam[3], tuple(cam[4:9]))
+        assert np.array_equal(o.view(np.uint32), xy.view(np.uint32)), ci
+        if cv2_ref.HAVE_CV2:
+            import cv2
+            K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+            live = cv2.undistortPoints(uv.reshape(-1, 1, 2), K, cam[4:9].astype(np.float32).reshape(1, 5)).reshape(-1, 2)
+            assert np.array_equal(live.view(np.uint32), xy.view(np.uint32)), ci
+
+
 def test_lk_oracle_argument_errors_and_empty():
     a = load_gray("kitti0.png")
     with pytest.raises(ValueError):

@@ -34,6 +34,29 @@ constexpr int CHAINS = 8;
         if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;                                     \
     }
 
+#define BODY_KERNEL_POST(NAME, DECL, STMT, POST)                                                        \
+    __global__ void __launch_bounds__(1024) NAME(unsigned* out, long long* cyc, unsigned seed) \
+    {                                                                                        \
+        __shared__ unsigned sm[4096];                                                        \
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i * seed;               \
+        __syncthreads();                                                                     \
+        unsigned a[CHAINS];                                                                  \
+        for (int k = 0; k < CHAINS; k++) a[k] = threadIdx.x * 7 + k + seed;                  \
+        unsigned b = seed | 1, c = seed * 3 + threadIdx.x;                                   \
+        const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);                         \
+        DECL;                                                                                \
+        long long t0 = clock64();                                                            \
+        for (int it = 0; it < ITERS; it++) {                                                 \
+            _Pragma("unroll") for (int k = 0; k < CHAINS; k++) { STMT; }                     \
+        }                                                                                    \
+        long long t1 = clock64();                                                            \
+        POST;                                                                                \
+        unsigned r = 0;                                                                      \
+        for (int k = 0; k < CHAINS; k++) r ^= a[k];                                          \
+        out[blockIdx.x * blockDim.x + threadIdx.x] = r + b + c;                              \
+        if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;                                     \
+    }
+
 BODY_KERNEL(k_imad, , asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c)))
 BODY_KERNEL(k_iadd3, , asm volatile("add.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(b)))
 BODY_KERNEL(k_lop3, , asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b), "r"(c)))
@@ -67,6 +90,19 @@ BODY_KERNEL(k_i2f64, , asm volatile("{ .reg .f64 d; cvt.rn.f64.s32 d, %0; cvt.rn
 BODY_KERNEL(k_fadd, float fc = 1e-9f, asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a[k]) : "f"(fc)))
 BODY_KERNEL(k_isetp_sel, , asm volatile("{ .reg .pred p; setp.gt.s32 p, %0, %1; selp.s32 %0, %1, %2, p; }" : "+r"(a[k]) : "r"(b), "r"(c)))
 
+BODY_KERNEL_POST(k_fadd2, unsigned long long fa2[CHAINS]; for (int k = 0; k < CHAINS; k++) fa2[k] = ((unsigned long long)a[k] << 32) | 0x3f800000u; unsigned long long fc2 = 0x3089705f3089705full, asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(fa2[k]) : "l"(fc2)), for (int k = 0; k < CHAINS; k++) a[k] ^= (unsigned)(fa2[k] >> 32) ^ (unsigned)fa2[k])
+BODY_KERNEL_POST(k_ffma2, unsigned long long fa2[CHAINS]; for (int k = 0; k < CHAINS; k++) fa2[k] = ((unsigned long long)a[k] << 32) | 0x3f800000u; unsigned long long fc2 = 0x3089705f3089705full; unsigned long long fb2 = 0x3f8000013f800001ull, asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(fa2[k]) : "l"(fb2), "l"(fc2)), for (int k = 0; k < CHAINS; k++) a[k] ^= (unsigned)(fa2[k] >> 32) ^ (unsigned)fa2[k])
+BODY_KERNEL(k_fadd_rm, float fc = 12582912.f, asm volatile("add.rm.f32 %0, %0, %1;" : "+r"(a[k]) : "f"(fc)))
+BODY_KERNEL_POST(k_imad_wide, unsigned long long wa[CHAINS]; for (int k = 0; k < CHAINS; k++) wa[k] = a[k], asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(wa[k]) : "r"((int)wa[k]), "r"(c)), for (int k = 0; k < CHAINS; k++) a[k] ^= (unsigned)(wa[k] >> 32) ^ (unsigned)wa[k])
+BODY_KERNEL(k_lea, , asm volatile("{ .reg .u32 t; shl.b32 t, %0, 7; add.u32 %0, t, %1; }" : "+r"(a[k]) : "r"(c)))
+BODY_KERNEL(k_mix_idp_lop, , asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(b), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[(k + 1) & 7]) : "r"(b), "r"(c)))
+BODY_KERNEL(k_mix_idp_iadd, , asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(b), "r"(c)); asm volatile("add.s32 %0, %0, %1;" : "+r"(a[(k + 1) & 7]) : "r"(b)))
+BODY_KERNEL(k_mix_idp_fadd, float fc = 1e-9f, asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(b), "r"(c)); asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a[(k + 1) & 7]) : "f"(fc)))
+BODY_KERNEL(k_mix_idp_2fadd, float fc = 1e-9f, asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(b), "r"(c)); asm volatile("add.rn.f32 %0, %0, %2; add.rn.f32 %1, %1, %2;" : "+r"(a[(k + 1) & 7]), "+r"(a[(k + 3) & 7]) : "f"(fc)))
+BODY_KERNEL(k_mix_lop_iadd, , asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b), "r"(c)); asm volatile("add.s32 %0, %0, %1;" : "+r"(a[(k + 1) & 7]) : "r"(b)))
+BODY_KERNEL(k_sgxt, , asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; cvt.s32.s16 %0, t; }" : "+r"(a[k]) : "r"(b)))
+BODY_KERNEL(k_lds64_x, unsigned base = smb + (threadIdx.x & 31) * 8, asm volatile("{ .reg .u32 t, u, v; add.u32 t, %1, %2; ld.shared.v2.u32 {u, v}, [t]; xor.b32 %0, %0, u; xor.b32 %0, %0, v; }" : "+r"(a[k]) : "r"(base), "r"((unsigned)(k * 256))))
+
 struct Entry { const char* name; void (*fn)(unsigned*, long long*, unsigned); int instr_per_stmt; };
 
 int main()
@@ -90,6 +126,9 @@ int main()
         {"isetp+sel", k_isetp_sel, 2},
         {"mix imad+shf", k_mix_imad_shf, 2}, {"mix 2dp2a+shr+2imad", k_mix_dp2a_shr_imad, 5},
         {"mix 4imad+shr+2imad", k_mix_4imad_shr_2imad, 7}, {"mix 4ffma+2imad", k_mix_ffma4_imad2, 6},
+        {"fadd2", k_fadd2, 1}, {"ffma2", k_ffma2, 1}, {"fadd.rm", k_fadd_rm, 1}, {"imad.wide", k_imad_wide, 1},
+        {"shl+add (lea?)", k_lea, 1}, {"mix idp+lop3", k_mix_idp_lop, 2}, {"mix idp+iadd", k_mix_idp_iadd, 2},
+        {"mix idp+fadd", k_mix_idp_fadd, 2}, {"mix idp+2fadd", k_mix_idp_2fadd, 3}, {"mix lop3+iadd", k_mix_lop_iadd, 2}, {"add+cvt.s32.s16", k_sgxt, 2},
     };
     for (auto& t : tests) {
         for (int warps : {32, 16}) {
