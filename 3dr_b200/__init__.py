@@ -33,6 +33,8 @@ SYMBOLS = [
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
     "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
+    "dr3lk_multi_create", "dr3lk_multi_destroy", "dr3lk_multi_size", "dr3lk_multi_context", "dr3lk_multi_last_error", "dr3lk_shard_range",
+    "dr3lk_multi_track_batch_host",
 ]
 
 
@@ -82,6 +84,19 @@ def lib():
                                     c_void_p, c_void_p, c_void_p, c_void_p] + lk_tail
     L.dr3lk_track_batch_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
+    if hasattr(L, "dr3lk_multi_create"):  # absent only in older builds loaded through DR3LK_LIB for A/B runs
+        L.dr3lk_multi_create.argtypes = [P(c_void_p), P(c_int), c_int]
+        L.dr3lk_multi_destroy.argtypes = [c_void_p]
+        L.dr3lk_multi_destroy.restype = None
+        L.dr3lk_multi_size.argtypes = [c_void_p]
+        L.dr3lk_multi_context.argtypes = [c_void_p, c_int]
+        L.dr3lk_multi_context.restype = c_void_p
+        L.dr3lk_multi_last_error.argtypes = [c_void_p]
+        L.dr3lk_multi_last_error.restype = ctypes.c_char_p
+        L.dr3lk_shard_range.argtypes = [c_int, c_int, c_int, P(c_int), P(c_int)]
+        L.dr3lk_shard_range.restype = None
+        L.dr3lk_multi_track_batch_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail
     L.dr3lk_lk_level_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, P(c_int), P(c_int)]
     L.dr3lk_build_lk_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, P(c_void_p),
                                          P(c_void_p), P(c_int)]
@@ -93,7 +108,7 @@ def lib():
     if hasattr(L, "dr3lk_track_frame"):  # absent only in older builds loaded through DR3LK_LIB for A/B runs
         L.dr3lk_track_frame.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int] + lk_tail + [c_int, P(c_void_p)]
     L.dr3lk_filter_tracks.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, P(c_int)]
+                                      c_void_p, c_void_p, c_void_p, c_void_p, P(c_int)]
     L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, P(c_int)]
     L.dr3lk_score_fundamental.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p, P(c_int)]
@@ -299,9 +314,10 @@ class Context:
             float(min_eig_threshold), keep_next, ctypes.byref(out) if keep_next else None))
         return npts, status, err, (Pyramid._wrap(self, out, win, prev_pyr.shape) if keep_next else None)
 
-    def filter_tracks(self, ref_pts, cur_pts, status, fx=None, fy=None, cx=0.0, cy=0.0):
+    def filter_tracks(self, ref_pts, cur_pts, status, fx=None, fy=None, cx=0.0, cy=0.0, dist=None):
         """Reference src/initialization.cpp:615-635: drop status == 0 (order kept), disparity norms and, when a pinhole
-        (fx, fy, cx, cy) is given, unit bearing vectors of the current points. Returns (ref, cur, disparity, bearing|None)."""
+        (fx, fy, cx, cy[, dist = (d0..d4)]) is given, unit bearing vectors of the current points (Pinhole::cam2world,
+        src/camera.cpp:25-41, both branches). Returns (ref, cur, disparity, bearing|None)."""
         r = np.ascontiguousarray(np.asarray(ref_pts, np.float32).reshape(-1, 2))
         c = np.ascontiguousarray(np.asarray(cur_pts, np.float32).reshape(-1, 2))
         st = np.ascontiguousarray(np.asarray(status, np.uint8))
@@ -311,8 +327,11 @@ class Context:
         disp = np.zeros(n, np.float64)
         bear = np.zeros((n, 3), np.float64) if fx is not None else None
         k = ctypes.c_int(0)
+        d5 = np.ascontiguousarray(dist, np.float64) if dist is not None else None
+        assert d5 is None or d5.shape == (5,)
         self._check(lib().dr3lk_filter_tracks(self._h, r.ctypes.data, c.ctypes.data, st.ctypes.data, n, float(fx or 1.0), float(fy or 1.0),
-                                              float(cx), float(cy), o_r.ctypes.data, o_c.ctypes.data, disp.ctypes.data,
+                                              float(cx), float(cy), d5.ctypes.data if d5 is not None else None,
+                                              o_r.ctypes.data, o_c.ctypes.data, disp.ctypes.data,
                                               bear.ctypes.data if bear is not None else None, ctypes.byref(k)))
         k = k.value
         return o_r[:k], o_c[:k], disp[:k], (bear[:k] if bear is not None else None)
@@ -386,6 +405,77 @@ class Context:
             stats.ctypes.data if stats is not None else None, chunk_pairs, win[0], win[1], max_level, criteria[0],
             criteria[1], float(criteria[2]), flags, float(min_eig_threshold)))
         return npts, status, err, stats
+
+
+class MultiContext:
+    """One context + one worker thread per listed device (dr3lk_multi): the host-buffer batch sharded by frame pair over
+    several GPUs from ONE process, results bit-identical to a single-device call."""
+
+    def __init__(self, devices):
+        devs = (ctypes.c_int * len(devices))(*devices)
+        self._h = ctypes.c_void_p()
+        rc = lib().dr3lk_multi_create(ctypes.byref(self._h), devs, len(devices))
+        if rc != OK:
+            raise Dr3lkError(rc, lib().dr3lk_multi_last_error(None).decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dr3lk_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def launch_count(self):
+        return sum(int(lib().dr3lk_launch_count(lib().dr3lk_multi_context(self._h, i))) for i in range(len(self.devices)))
+
+    def track_batch_host(self, prev, nxt, prev_pts, pts_offset, next_pts=None, win=(21, 21), max_level=3,
+                         criteria=(TERM_COUNT | TERM_EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4, want_err=True,
+                         want_stats=False, chunk_pairs=0, out=None):
+        """Same arguments and results as Context.track_batch_host."""
+        prev, nxt = np.asarray(prev), np.asarray(nxt)
+        assert prev.dtype == np.uint8 and prev.ndim == 3 and prev.shape == nxt.shape and prev.strides == nxt.strides
+        assert prev.strides[2] == 1
+        B, h, w = prev.shape
+        offs = np.ascontiguousarray(np.asarray(pts_offset, np.int32))
+        pp = np.asarray(prev_pts, np.float32).reshape(-1, 2)
+        assert pp.flags.c_contiguous
+        n = pp.shape[0]
+        if out is not None:
+            npts, status, err, stats = out
+        else:
+            npts = np.zeros((n, 2), np.float32)
+            status = np.zeros(n, np.uint8)
+            err = np.zeros(n, np.float32) if want_err else None
+            stats = np.zeros(n, np.uint32) if want_stats else None
+        if flags & USE_INITIAL_FLOW:
+            npts[...] = np.asarray(next_pts, np.float32).reshape(-1, 2)
+        rc = lib().dr3lk_multi_track_batch_host(
+            self._h, prev.ctypes.data, nxt.ctypes.data, w, h, prev.strides[1], prev.strides[0], B, pp.ctypes.data,
+            npts.ctypes.data, status.ctypes.data, err.ctypes.data if err is not None else None, offs.ctypes.data,
+            stats.ctypes.data if stats is not None else None, chunk_pairs, win[0], win[1], max_level, criteria[0],
+            criteria[1], float(criteria[2]), flags, float(min_eig_threshold))
+        if rc != OK:
+            raise Dr3lkError(rc, lib().dr3lk_multi_last_error(self._h).decode())
+        return npts, status, err, stats
+
+
+def shard_range(n_pairs, rank, world):
+    """dr3lk_shard_range: the contiguous block of pairs rank `rank` of `world` owns."""
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    lib().dr3lk_shard_range(n_pairs, rank, world, ctypes.byref(lo), ctypes.byref(hi))
+    return lo.value, hi.value
 
 
 class Pyramid:

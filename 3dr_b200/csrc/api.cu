@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dr3lk_internal.cuh"
@@ -124,6 +125,8 @@ struct dr3lk_ctx {
     Workspace ws;                 // single-call / device-batch scratch
     HostBuf pinned;               // staging for the single-pair host call
     std::vector<DevBuf> pool;     // device buffers of destroyed dr3lk_pyramid objects, reused by the next create
+    std::vector<struct dr3lk_pyramid*> live;  // pyramid objects of this context that have not been destroyed yet: dr3lk_destroy
+                                              // frees their device buffers and orphans them (ctx = nullptr), see dr3lk.h
     DevBuf take(size_t bytes)
     {
         for (size_t i = 0; i < pool.size(); i++)
@@ -377,11 +380,14 @@ int dr3lk_create(dr3lk_ctx** out, int device)
     return DR3LK_OK;
 }
 
+static void orphan_pyramids(dr3lk_ctx* ctx);
+
 void dr3lk_destroy(dr3lk_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    orphan_pyramids(ctx);
     ctx->ws.release();
     ctx->pinned.release();
     for (auto& b : ctx->pool) b.release();
@@ -398,7 +404,14 @@ const char* dr3lk_last_error(const dr3lk_ctx* ctx) { return ctx ? ctx->err.c_str
 int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return DR3LK_E_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t want = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (want != ctx->stream) {
+        // Scratch state is ordered by the stream it was last used on (cleared derivative aprons, the LK work counters,
+        // pooled pyramid buffers): finish that work before anything is enqueued on another stream.
+        cudaSetDevice(ctx->device);
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stream = want;
+    }
     return DR3LK_OK;
 }
 
@@ -496,6 +509,7 @@ int dr3lk_box_pyramid_device(dr3lk_ctx* ctx, const uint8_t* img_dev, int w, int 
     if (!ctx) return DR3LK_E_ARG;
     if (!img_dev || n_levels < 1 || batch < 1 || (n_levels > 1 && !out_levels_dev)) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad argument");
     if (mode < DR3LK_BOX_AUTO_X86 || mode > DR3LK_BOX_SSE2) return fail(ctx, DR3LK_E_ARG, "box pyramid: bad mode");
+    if (batch > 65535) return fail(ctx, DR3LK_E_SIZE, "box pyramid: at most 65535 images per call (the image index is gridDim.y): split the batch");
     cudaSetDevice(ctx->device);
     Launch L{ctx->stream, cudaSuccess, 0};
     const uint8_t* src = img_dev;
@@ -666,6 +680,12 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     cudaSetDevice(ctx->device);
     for (int i = 0; i < dr3lk_ctx::kSlots; i++)
         if (!ctx->slot_stream[i]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
+    // Whatever way this function returns, no copy may still be in flight: earlier chunks read `offs_host` (a local) and write
+    // the caller's output buffers.  The guard drains the slot streams on every exit, error returns included.
+    struct Drain {
+        dr3lk_ctx* c;
+        ~Drain() { for (int i = 0; i < dr3lk_ctx::kSlots; i++) if (c->slot_stream[i]) cudaStreamSynchronize(c->slot_stream[i]); }
+    } drain{ctx};
     // the pipeline streams start after whatever the caller queued on the context stream ...
     cudaEvent_t ev_start;
     CU_TRY(ctx, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
@@ -740,6 +760,96 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         cudaEventDestroy(ev);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DR3LK_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* multi-GPU: one context + one worker thread per device, contiguous blocks of frame pairs          */
+/* ---------------------------------------------------------------------------------------------- */
+
+struct dr3lk_multi {
+    std::vector<dr3lk_ctx*> ctx;   // one per entry of `devices` (a device may be listed more than once)
+    std::string err;
+};
+
+int dr3lk_multi_create(dr3lk_multi** out, const int* devices, int n_devices)
+{
+    if (!out) return DR3LK_E_ARG;
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > 64) { g_create_error = "multi_create: 1..64 devices"; return DR3LK_E_ARG; }
+    dr3lk_multi* m = new (std::nothrow) dr3lk_multi();
+    if (!m) return DR3LK_E_CUDA;
+    for (int i = 0; i < n_devices; i++) {
+        dr3lk_ctx* c = nullptr;
+        const int rc = dr3lk_create(&c, devices[i]);
+        if (rc != DR3LK_OK) {
+            for (dr3lk_ctx* x : m->ctx) dr3lk_destroy(x);
+            delete m;
+            return rc;  // g_create_error was set by dr3lk_create
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return DR3LK_OK;
+}
+
+void dr3lk_multi_destroy(dr3lk_multi* m)
+{
+    if (!m) return;
+    for (dr3lk_ctx* c : m->ctx) dr3lk_destroy(c);
+    delete m;
+}
+
+int dr3lk_multi_size(const dr3lk_multi* m) { return m ? (int)m->ctx.size() : 0; }
+dr3lk_ctx* dr3lk_multi_context(dr3lk_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+const char* dr3lk_multi_last_error(const dr3lk_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+void dr3lk_shard_range(int n_pairs, int rank, int world, int* lo, int* hi)
+{
+    // pair p lives on rank floor(p * world / n_pairs): contiguous blocks, the same rule as 3dr_b200/sharding.py
+    *lo = (int)(((long long)rank * n_pairs) / world);
+    *hi = (int)(((long long)(rank + 1) * n_pairs) / world);
+}
+
+int dr3lk_multi_track_batch_host(dr3lk_multi* m, const uint8_t* prev, const uint8_t* next, int w, int h, size_t step, size_t image_stride,
+                                 int batch, const float* prev_pts, float* next_pts, uint8_t* status, float* err, const int* pts_offset,
+                                 uint32_t* stats, int chunk_pairs, int win_w, int win_h, int max_level, int crit_type, int crit_max_count,
+                                 double crit_eps, int flags, double min_eig_threshold)
+{
+    if (!m) return DR3LK_E_ARG;
+    const int G = (int)m->ctx.size();
+    // argument errors are reported once, by the first context, before any thread starts
+    if (batch < 1 || !pts_offset) { m->err = "multi_track_batch_host: bad batch / offsets"; return DR3LK_E_ARG; }
+    {
+        int rc = check_offsets(m->ctx[0], pts_offset, batch);
+        if (rc != DR3LK_OK) { m->err = m->ctx[0]->err; return rc; }
+    }
+    std::vector<int> rcs(G, DR3LK_OK);
+    std::vector<std::vector<int>> offs(G);
+    std::vector<std::thread> workers;
+    workers.reserve(G);
+    for (int r = 0; r < G; r++) {
+        int lo, hi;
+        dr3lk_shard_range(batch, r, G, &lo, &hi);
+        if (hi <= lo) continue;
+        const int p0 = pts_offset[lo];
+        offs[r].resize(hi - lo + 1);
+        for (int b = lo; b <= hi; b++) offs[r][b - lo] = pts_offset[b] - p0;
+        // every rank owns disjoint slices of the caller's arrays: no exchange, no lock (the "final gather" of SURVEY.md 8e is
+        // each device's own D2H copy into its slice)
+        workers.emplace_back([=, &rcs, &offs]() {
+            rcs[r] = dr3lk_track_batch_host(m->ctx[r], prev + (size_t)lo * image_stride, next + (size_t)lo * image_stride, w, h, step,
+                                            image_stride, hi - lo, prev_pts + 2 * (size_t)p0, next_pts + 2 * (size_t)p0, status + p0,
+                                            err ? err + p0 : nullptr, offs[r].data(), stats ? stats + p0 : nullptr, chunk_pairs, win_w,
+                                            win_h, max_level, crit_type, crit_max_count, crit_eps, flags, min_eig_threshold);
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int r = 0; r < G; r++)
+        if (rcs[r] != DR3LK_OK) {
+            m->err = "device " + std::to_string(m->ctx[r]->device) + " (rank " + std::to_string(r) + "): " + m->ctx[r]->err;
+            return rcs[r];
+        }
     return DR3LK_OK;
 }
 
@@ -821,8 +931,20 @@ static int pyramid_alloc(dr3lk_ctx* ctx, int w, int h, int win_w, int win_h, int
         d.dpitch = P.dpitch[l];
         d.deriv_stride = (unsigned)P.der_ints[l];
     }
+    ctx->live.push_back(p);
     *out = p;
     return DR3LK_OK;
+}
+
+// dr3lk_destroy: pyramid objects that outlive their context keep a valid handle (so that dr3lk_pyramid_destroy stays legal in
+// any order, e.g. from a garbage collector or a static destructor) but lose their device memory and their context.
+static void orphan_pyramids(dr3lk_ctx* ctx)
+{
+    for (dr3lk_pyramid* p : ctx->live) {
+        p->img.release(); p->deriv.release();
+        p->ctx = nullptr;
+    }
+    ctx->live.clear();
 }
 
 // Enqueues the build of a pyramid object from a level-0 image that is already on the device (16-B pitched scratch,
@@ -862,6 +984,8 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
 static void pyramid_free(dr3lk_pyramid* p, bool to_pool)
 {
     dr3lk_ctx* ctx = p->ctx;
+    if (!ctx) { delete p; return; }  // orphaned by dr3lk_destroy: the device buffers are gone already
+    ctx->live.erase(std::remove(ctx->live.begin(), ctx->live.end(), p), ctx->live.end());
     if (to_pool && ctx->pool.size() < 16) {
         if (p->img.p) ctx->pool.push_back(p->img);
         if (p->deriv.p) ctx->pool.push_back(p->deriv);
@@ -905,7 +1029,7 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
 void dr3lk_pyramid_destroy(dr3lk_pyramid* pyr)
 {
     if (!pyr) return;
-    cudaSetDevice(pyr->ctx->device);
+    if (pyr->ctx) cudaSetDevice(pyr->ctx->device);
     // stream-ordered reuse is safe: every consumer of these buffers was enqueued on the context's stream before this point
     pyramid_free(pyr, true);
 }
@@ -1050,7 +1174,8 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
 /* ---------------------------------------------------------------------------------------------- */
 
 int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_pts, const uint8_t* status, int n, double fx, double fy,
-                        double cx, double cy, float* out_ref, float* out_cur, double* out_disparity, double* out_bearing, int* n_kept)
+                        double cx, double cy, const double* distortion, float* out_ref, float* out_cur, double* out_disparity,
+                        double* out_bearing, int* n_kept)
 {
     if (!ctx) return DR3LK_E_ARG;
     if (n < 0 || !n_kept) return fail(ctx, DR3LK_E_ARG, "filter_tracks: bad argument");
@@ -1074,7 +1199,7 @@ int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_p
     memcpy(hp + i_st, status, (size_t)n);
     CU_TRY(ctx, cudaMemcpyAsync(dp, hp, o_ref, cudaMemcpyHostToDevice, st));
     Launch L{st, cudaSuccess, 0};
-    launch_filter_tracks(L, (const float*)(dp + i_ref), (const float*)(dp + i_cur), dp + i_st, n, fx, fy, cx, cy, (float*)(dp + o_ref),
+    launch_filter_tracks(L, (const float*)(dp + i_ref), (const float*)(dp + i_cur), dp + i_st, n, fx, fy, cx, cy, distortion, (float*)(dp + o_ref),
                          (float*)(dp + o_cur), (double*)(dp + o_disp), out_bearing ? (double*)(dp + o_bear) : nullptr, (int*)(dp + o_cnt));
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "filter kernel launch");

@@ -96,7 +96,7 @@ void launch_fast_gather(Launch& L, const unsigned long long* cell_best, int n_ce
 
 // filter.cu
 void launch_filter_tracks(Launch& L, const float* ref, const float* cur, const uint8_t* status, int n, double fx, double fy, double cx,
-                          double cy, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept);
+                          double cy, const double* dist5 /* host, 5 doubles or null */, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept);
 
 void launch_score_fundamental(Launch& L, const float* F, int n_hyp, const float* p1, const float* p2, int n, float inv_sigma2,
                               float* scores, uint8_t* inliers);

@@ -1,5 +1,7 @@
 // the post-filter right behind the LK call (reference src/initialization.cpp:615-635): stable
 // compaction of the tracked points, disparity norm and pinhole bearing vectors, one kernel.
+#include <math.h>
+
 #include "dr3lk_internal.cuh"
 
 namespace dr3lk {
@@ -8,11 +10,48 @@ namespace {
 
 constexpr int FT = 1024;
 
+// Pinhole::cam2world for a camera WITH distortion (reference src/camera.cpp:32-40): cv::undistortPoints on the float pixel
+// with the float K / D the constructor builds (src/camera.cpp:19-20), no R / P, default criteria = 5 fixed-point iterations.
+// OpenCV's cvUndistortPointsInternal works in double and rounds the result to float; the statement order below is its own
+// (terms of the unused coefficients k5..k11 are kept as the +0 they evaluate to, so signed zeros come out the same).
+struct Distortion {
+    double k[5];  // (double)(float)d0 .. d4
+    double fx, fy, cx, cy;  // (double)(float) of the intrinsics: _cvK is a float matrix
+    int on;       // Pinhole::_distortion = fabs(d0) > 1e-7 (src/camera.cpp:17)
+};
+
+__device__ __forceinline__ void undistort_point(const Distortion& D, float uf, float vf, double& xo, double& yo)
+{
+    const double ifx = __ddiv_rn(1.0, D.fx), ify = __ddiv_rn(1.0, D.fy);
+    const double u = (double)uf, v = (double)vf;
+    double x = __dmul_rn(__dsub_rn(u, D.cx), ifx), y = __dmul_rn(__dsub_rn(v, D.cy), ify);
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double zero3 = __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(0.0, r2), 0.0), r2), 0.0), r2);  // ((k7 r2 + k6) r2 + k5) r2
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(D.k[4], r2), D.k[1]), r2), D.k[0]), r2));
+        const double icdist = __ddiv_rn(__dadd_rn(1.0, zero3), den);
+        if (icdist < 0) {
+            x = __dmul_rn(__dsub_rn(u, D.cx), ifx);
+            y = __dmul_rn(__dsub_rn(v, D.cy), ify);
+            break;
+        }
+        const double z1 = __dmul_rn(0.0, r2), z2 = __dmul_rn(__dmul_rn(0.0, r2), r2);  // k8 r2, k9 r2 r2 (and k10, k11)
+        const double xy2k2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, D.k[2]), x), y), xy2k3 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, D.k[3]), x), y);
+        const double dX = __dadd_rn(__dadd_rn(__dadd_rn(xy2k2, __dmul_rn(D.k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))), z1), z2);
+        const double dY = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(D.k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), xy2k3), z1), z2);
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    xo = (double)(float)x;  // dst is CV_32FC2, cam2world promotes px.x / px.y back to double
+    yo = (double)(float)y;
+}
+
 // Single CTA (N is a few thousand at most on this path): per-thread status counts over contiguous slices, block scan,
 // then ordered scatter.  All double arithmetic uses explicitly rounded intrinsics so it matches a plain C evaluation.
 __global__ void __launch_bounds__(FT)
 filter_tracks_kernel(const float2* __restrict__ ref, const float2* __restrict__ cur, const uint8_t* __restrict__ status, int n,
-                     double fx, double fy, double cx, double cy, float2* __restrict__ out_ref, float2* __restrict__ out_cur,
+                     double fx, double fy, double cx, double cy, const Distortion dist, float2* __restrict__ out_ref, float2* __restrict__ out_cur,
                      double* __restrict__ out_disp, double* __restrict__ out_bearing, int* __restrict__ n_kept)
 {
     __shared__ int s_cnt[FT];
@@ -40,7 +79,9 @@ filter_tracks_kernel(const float2* __restrict__ ref, const float2* __restrict__ 
         const double dx = (double)__fsub_rn(r.x, q.x), dy = (double)__fsub_rn(r.y, q.y);
         out_disp[pos] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
         if (out_bearing) {
-            const double x = __ddiv_rn(__dsub_rn((double)q.x, cx), fx), y = __ddiv_rn(__dsub_rn((double)q.y, cy), fy);
+            double x, y;
+            if (dist.on) undistort_point(dist, q.x, q.y, x, y);
+            else { x = __ddiv_rn(__dsub_rn((double)q.x, cx), fx); y = __ddiv_rn(__dsub_rn((double)q.y, cy), fy); }
             const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), 1.0));
             out_bearing[3 * pos] = __ddiv_rn(x, nrm);
             out_bearing[3 * pos + 1] = __ddiv_rn(y, nrm);
@@ -117,10 +158,14 @@ void launch_score_fundamental(Launch& L, const float* F, int n_hyp, const float*
 }
 
 void launch_filter_tracks(Launch& L, const float* ref, const float* cur, const uint8_t* status, int n, double fx, double fy, double cx,
-                          double cy, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept)
+                          double cy, const double* dist5, float* out_ref, float* out_cur, double* out_disp, double* out_bearing, int* n_kept)
 {
     if (L.err != cudaSuccess) return;
-    filter_tracks_kernel<<<1, FT, 0, L.stream>>>((const float2*)ref, (const float2*)cur, status, n, fx, fy, cx, cy, (float2*)out_ref,
+    Distortion D;
+    D.on = dist5 != nullptr && fabs(dist5[0]) > 1e-7;
+    for (int i = 0; i < 5; i++) D.k[i] = dist5 ? (double)(float)dist5[i] : 0.0;
+    D.fx = (double)(float)fx; D.fy = (double)(float)fy; D.cx = (double)(float)cx; D.cy = (double)(float)cy;
+    filter_tracks_kernel<<<1, FT, 0, L.stream>>>((const float2*)ref, (const float2*)cur, status, n, fx, fy, cx, cy, D, (float2*)out_ref,
                                                (float2*)out_cur, out_disp, out_bearing, n_kept);
     L.err = cudaGetLastError();
     L.launches++;

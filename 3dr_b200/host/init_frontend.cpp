@@ -90,7 +90,11 @@ int main(int argc, char** argv)
                 ++outlier_count;
                 continue;
             }
-            disparities.push_back(std::hypot(static_cast<double>(ref_it->x) - cur_it->x, static_cast<double>(ref_it->y) - cur_it->y));
+            // Vector2d(ref.x - cur.x, ref.y - cur.y).norm(): the differences are FLOAT subtractions (cv::Point2f members)
+            // promoted to double, then sqrt(x*x + y*y) -- src/initialization.cpp:629-630; same as filter.cu / oracle/postfilter.py
+            const float dxf = ref_it->x - cur_it->x, dyf = ref_it->y - cur_it->y;
+            const double dx = dxf, dy = dyf;
+            disparities.push_back(std::sqrt(dx * dx + dy * dy));
             ++ref_it;
             ++cur_it;
         }

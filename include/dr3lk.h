@@ -48,7 +48,9 @@ typedef struct dr3lk_ctx dr3lk_ctx;
 int dr3lk_create(dr3lk_ctx** out, int device);
 void dr3lk_destroy(dr3lk_ctx* ctx);
 const char* dr3lk_last_error(const dr3lk_ctx* ctx); /* ctx may be NULL: message of the last failed create */
-/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream.  Switching to a
+ * different stream first waits for the work queued on the current one (the context's scratch buffers are ordered by the
+ * stream they were last used on). */
 int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream);
 int dr3lk_synchronize(dr3lk_ctx* ctx);
 /* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -110,6 +112,26 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
                            int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
                            double min_eig_threshold);
 
+/* ---- multi-GPU form of the host-buffer batch ---------------------------------------------------------- */
+/* The reference is one C++ process (src/handler.cpp:31-48); to use several GPUs from one process a dr3lk_multi owns one
+ * context per listed device (a device may be listed more than once) and dr3lk_multi_track_batch_host runs one worker
+ * thread per context.  Frame pairs are independent, so the batch is cut into contiguous blocks (dr3lk_shard_range: pair p
+ * belongs to rank floor(p * world / n_pairs)); every device builds the pyramids of its own pairs and copies its results
+ * straight into its slice of the caller's arrays: no collective, no exchange between devices.  Arguments and results are
+ * those of dr3lk_track_batch_host (bit-identical to a single-device call, whatever the number of devices). */
+typedef struct dr3lk_multi dr3lk_multi;
+int dr3lk_multi_create(dr3lk_multi** out, const int* devices, int n_devices);
+void dr3lk_multi_destroy(dr3lk_multi* m);
+int dr3lk_multi_size(const dr3lk_multi* m);
+dr3lk_ctx* dr3lk_multi_context(dr3lk_multi* m, int i); /* context of rank i (owned by m), e.g. for dr3lk_launch_count */
+const char* dr3lk_multi_last_error(const dr3lk_multi* m);
+void dr3lk_shard_range(int n_pairs, int rank, int world, int* lo, int* hi);
+int dr3lk_multi_track_batch_host(dr3lk_multi* m, const uint8_t* prev, const uint8_t* next, int w, int h, size_t step,
+                                 size_t image_stride, int batch, const float* prev_pts, float* next_pts, uint8_t* status,
+                                 float* err, const int* pts_offset, uint32_t* stats, int chunk_pairs, int win_w, int win_h,
+                                 int max_level, int crit_type, int crit_max_count, double crit_eps, int flags,
+                                 double min_eig_threshold);
+
 /* ---- the pyramids calcOpticalFlowPyrLK builds internally (buildOpticalFlowPyramid + calcScharrDeriv) ---- */
 /* Level sizes with OpenCV's early stop; ws/hs need max_level+1 entries.  Returns the effective maxLevel. */
 int dr3lk_lk_level_sizes(int w, int h, int win_w, int win_h, int max_level, int* ws, int* hs);
@@ -125,7 +147,11 @@ int dr3lk_build_lk_pyramid(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, siz
  * (src/initialization.cpp:608-609), so OpenCV rebuilds both Gaussian pyramids and the reference frame's Scharr
  * derivatives on every call -- also on every retry against the same reference frame (src/handler.cpp:67-72).
  * A dr3lk_pyramid is the device-resident equivalent of OpenCV's precomputed-pyramid input form: Gaussian levels
- * (with OpenCV's early stop for win/max_level) plus Scharr derivatives, built once per frame. */
+ * (with OpenCV's early stop for win/max_level) plus Scharr derivatives, built once per frame.
+ * Lifetime: a pyramid belongs to the context that created it.  dr3lk_destroy(ctx) releases the device memory of every
+ * pyramid of that context that is still alive and orphans it: the handle stays valid for exactly one thing,
+ * dr3lk_pyramid_destroy (any order of destruction is legal, e.g. from a garbage collector or a static destructor);
+ * every other call that is handed an orphaned pyramid fails with DR3LK_E_ARG. */
 typedef struct dr3lk_pyramid dr3lk_pyramid;
 int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int win_w, int win_h, int max_level,
                          dr3lk_pyramid** out);
@@ -151,12 +177,15 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
 
 /* f-3: the step right after the LK call, reference src/initialization.cpp:615-635 -- drop the points with status == 0
  * (order preserved, like the erase loop), disparity = ||ref - cur|| (double), and the unit bearing vector of the current
- * point for an undistorted pinhole camera ((u-cx)/fx, (v-cy)/fy, 1) normalised (src/camera.cpp:25-41, !_distortion).
+ * point, Pinhole::cam2world (src/camera.cpp:25-41): ((u-cx)/fx, (v-cy)/fy, 1) normalised for an undistorted camera; with
+ * distortion (d0..d4 = k1 k2 p1 p2 k3 in `distortion`, active when fabs(d0) > 1e-7 like Pinhole::_distortion,
+ * src/camera.cpp:17) the pixel first goes through cv::undistortPoints' five fixed-point iterations with the float K / D the
+ * reference's constructor builds.  distortion may be NULL (= undistorted).
  * Host buffers; out_ref/out_cur hold n x 2 floats, out_disparity n doubles, out_bearing n x 3 doubles (may be NULL).
  * *n_kept receives the number of surviving points. */
 int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_pts, const uint8_t* status, int n, double fx,
-                        double fy, double cx, double cy, float* out_ref, float* out_cur, double* out_disparity,
-                        double* out_bearing, int* n_kept);
+                        double fy, double cx, double cy, const double* distortion, float* out_ref, float* out_cur,
+                        double* out_disparity, double* out_bearing, int* n_kept);
 
 /* f-1 / a-10: the prevPts provider -- feature_detection::FastDetector::detect (reference src/features.cpp:43-98) on
  * the Frame's box pyramid (utils::create_img_pyramid, n_levels levels, rounding `box_mode`): FAST-10 corners

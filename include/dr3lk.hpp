@@ -11,6 +11,7 @@
 #define DR3LK_HPP_
 
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -83,10 +84,18 @@ public:
     {
         if (rc != DR3LK_OK) throw Exception(rc, dr3lk_last_error(ctx_));
     }
+    // The context the free functions use when none is passed: one per calling thread, on the CUDA device named by the
+    // environment variable DR3LK_DEVICE (default 0) -- the reference has no notion of a device, so the selection has to
+    // live outside its call surface.
     static Context& thread_default()
     {
-        static thread_local Context c(0);
+        static thread_local Context c(default_device());
         return c;
+    }
+    static int default_device()
+    {
+        const char* e = std::getenv("DR3LK_DEVICE");
+        return e && *e ? std::atoi(e) : 0;
     }
 
 private:
@@ -222,12 +231,13 @@ inline std::unique_ptr<Pyramid> trackFrame(const Pyramid& prevPyr, const Image& 
 }
 
 // ---- the erase-by-status loop of src/initialization.cpp:615-635 in one call ----
-// Removes the lost points from ref/cur (order kept), fills the disparities and, for an undistorted pinhole, the unit
-// bearing vectors of the current points (3 doubles each; pass fx = 0 to skip them).
+// Removes the lost points from ref/cur (order kept), fills the disparities and the unit bearing vectors of the current
+// points (3 doubles each; pass fx = 0 to skip them) -- Pinhole::cam2world, src/camera.cpp:25-41: `distortion` = the
+// camera's d0..d4 (nullptr or |d0| <= 1e-7: the undistorted branch).
 template <class P2f>
 inline void filterTracks(std::vector<P2f>& kpsRef, std::vector<P2f>& kpsCur, const std::vector<unsigned char>& status,
                          std::vector<double>& disparities, std::vector<double>& bearings, double fx = 0, double fy = 0, double cx = 0,
-                         double cy = 0, Context* context = nullptr)
+                         double cy = 0, Context* context = nullptr, const double* distortion = nullptr)
 {
     static_assert(sizeof(P2f) == 2 * sizeof(float), "points must be two packed floats (x, y)");
     Context& c = context ? *context : Context::thread_default();
@@ -237,7 +247,7 @@ inline void filterTracks(std::vector<P2f>& kpsRef, std::vector<P2f>& kpsCur, con
     bearings.assign(fx != 0 ? 3 * kpsRef.size() : 0, 0.0);
     int kept = 0;
     c.check(dr3lk_filter_tracks(c.get(), reinterpret_cast<const float*>(kpsRef.data()), reinterpret_cast<const float*>(kpsCur.data()),
-                                status.data(), n, fx != 0 ? fx : 1.0, fy != 0 ? fy : 1.0, cx, cy, reinterpret_cast<float*>(r.data()),
+                                status.data(), n, fx != 0 ? fx : 1.0, fy != 0 ? fy : 1.0, cx, cy, distortion, reinterpret_cast<float*>(r.data()),
                                 reinterpret_cast<float*>(q.data()), disparities.data(), fx != 0 ? bearings.data() : nullptr, &kept));
     r.resize(kept); q.resize(kept); disparities.resize(kept);
     if (fx != 0) bearings.resize(3 * static_cast<size_t>(kept));

@@ -44,6 +44,15 @@ def golden_case(name):
 GOLDEN_CASES = ["c1_default_21x21", "c1_reference_30x30_initflow", "c1_31x31_L4", "c1_mineig_21x21", "oddwidth_21x21",
                 "c1_noisy_init_15x9"]
 
+# Position parity against cv2 over ALL jointly tracked points of each golden case (4907 points each), not only the ones that
+# converged before the iteration cap: (points allowed over 0.01 px, bound on the largest difference in px).  Measured (oracle ==
+# GPU bit for bit): 1 / 0.0105, 0 / -, 2 / 0.072, 1 / 0.0105, 1 / 0.012, 13 / 12.6.  The outliers are points whose level-0
+# loop ran into the iteration cap (or, for the 15x9 case with a 1.5 px noisy initial flow, hopped between two local minima):
+# x86 OpenCV sums the 2x2 system in fp32 SIMD lanes, the oracle and the GPU sum the same integer products exactly, and a
+# non-contracting iteration amplifies that last-bit difference.  Points that converge (level-0 loop ended before the cap) agree to <= 0.0082 px in every case.
+ALL_TRACKED_BOUNDS = {"c1_default_21x21": (1, 0.02), "c1_reference_30x30_initflow": (0, 0.01), "c1_31x31_L4": (2, 0.1),
+                      "c1_mineig_21x21": (1, 0.02), "oddwidth_21x21": (1, 0.02), "c1_noisy_init_15x9": (13, 13.0)}
+
 
 def golden_json(name):
     with open(os.path.join(GOLDEN, name)) as f:
@@ -66,6 +75,8 @@ def compare_lk(p_a, s_a, e_a, p_b, s_b, e_b, converged=None):
         "max_dpos_converged": float(d[both_c].max()) if both_c.any() else 0.0,
         "max_dpos_tracked": float(d[both].max()) if both.any() else 0.0,
         "frac_within_0p01": float((d[both] <= 0.01).mean()) if both.any() else 1.0,
+        "n_over_0p01_tracked": int((d[both] > 0.01).sum()),
+        "n_over_0p01_converged": int((d[both_c] > 0.01).sum()),
     }
     if e_a is not None and e_b is not None:
         de = np.abs(np.asarray(e_a, np.float64) - np.asarray(e_b, np.float64))

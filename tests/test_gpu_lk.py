@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from _common import GOLDEN_CASES, compare_lk, golden_case, golden_json, load_gray, random_points
+from _common import ALL_TRACKED_BOUNDS, GOLDEN_CASES, compare_lk, golden_case, golden_json, load_gray, random_points
 
 pytestmark = pytest.mark.gpu
 
@@ -30,7 +30,11 @@ def test_lk_matches_oracle_bit_exact_and_cv2_golden(ctx, case):
     _assert_bit_exact(got, (po, so, eo), case)
     max_count = min(max(g["crit"][1], 0), 100) if g["crit"][0] & 1 else 30
     m = compare_lk(got[0], got[1], got[2], g["next_pts"], g["status"], g["err"], tr["iters"][:, 0] < max_count)
-    assert m["status_agree"] >= 0.999 and m["max_dpos_converged"] <= 0.01 and m["frac_within_0p01"] >= 0.99, m
+    assert m["status_agree"] >= 0.999 and m["max_dpos_converged"] <= 0.01 and m["n_over_0p01_converged"] == 0, m
+    # all jointly tracked points, iteration-capped ones included: bounded count and size of the outliers (see _common.py)
+    n_over, max_d = ALL_TRACKED_BOUNDS[case]
+    print("%s: %d jointly tracked, %d over 0.01 px (max %.4f px)" % (case, m["n_both"], m["n_over_0p01_tracked"], m["max_dpos_tracked"]))
+    assert m["n_over_0p01_tracked"] <= n_over and m["max_dpos_tracked"] <= max_d and m["frac_within_0p01"] >= 0.997, m
 
 
 @pytest.mark.parametrize("win,ml,crit,flags", [

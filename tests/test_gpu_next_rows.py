@@ -94,6 +94,11 @@ def test_filter_tracks_matches_restatement(ctx):
         for a, b in zip(got, exp):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), n
         assert np.allclose(np.linalg.norm(got[3], axis=1), 1.0, atol=1e-15)
+        dist = (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)  # Pinhole with distortion, src/camera.cpp:32-40
+        got = ctx.filter_tracks(ref, cur, st, 458.654, 457.296, 367.215, 248.375, dist)
+        exp = postfilter.filter_tracks(ref, cur, st, 458.654, 457.296, 367.215, 248.375, dist)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), ("distorted", n)
     r, c, d, b = ctx.filter_tracks(ref, cur, np.zeros(len(ref), np.uint8))
     assert len(r) == 0 and len(d) == 0 and b is None
     r, c, d, b = ctx.filter_tracks(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.uint8))
@@ -164,3 +169,48 @@ def test_score_fundamental_matches_restatement(ctx):
     assert best == exp_best and np.nanmax(sc) > 0
     sc2, inl2, _ = ctx.score_fundamental(F[:3], p1[:5], p2[:5], 2.0, want_inliers=False)
     assert inl2 is None and np.array_equal(sc2, postfilter.check_fundamental(F[:3], p1[:5], p2[:5], 2.0)[0])
+
+
+def test_pyramid_outliving_its_context_is_safe(dr3):
+    """dr3lk.h lifetime rule: dr3lk_destroy orphans the pyramids that are still alive; destroying them afterwards is legal
+    (Python's garbage collector and C++ static destructors do exactly that), using them is an error, not a crash."""
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = random_points(np.random.default_rng(3), 1240, 376, 200)
+    c1 = dr3.Context(0)
+    p1, p2 = dr3.Pyramid(c1, a), dr3.Pyramid(c1, b)
+    exp = c1.calc_optical_flow_pyr_lk_cached(p1, p2, pts)
+    p2.close()               # normal order for one of them ...
+    c1.close()               # ... the other one outlives its context
+    c2 = dr3.Context(0)
+    q1, q2 = dr3.Pyramid(c2, a), dr3.Pyramid(c2, b)
+    with pytest.raises(dr3.Dr3lkError) as e:
+        c2.calc_optical_flow_pyr_lk_cached(p1, q2, pts)   # orphaned pyramid: refused
+    assert e.value.code == dr3.E_ARG
+    got = c2.calc_optical_flow_pyr_lk_cached(q1, q2, pts)
+    assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    p1.close()               # destroy after the context is gone: no use-after-free
+    p1.close()               # idempotent in the wrapper
+    q1.close(); q2.close(); c2.close()
+    for _ in range(20):      # contexts and pyramids created and dropped in every order
+        c = dr3.Context(0)
+        ps = [dr3.Pyramid(c, a) for _ in range(3)]
+        ps[0].close(); c.close(); ps[1].close()
+        del ps
+
+
+def test_set_stream_switch_keeps_results(ctx, dr3):
+    """dr3lk_set_stream joins the previous stream before switching: back-to-back calls on alternating streams stay bit-exact"""
+    import torch
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = random_points(np.random.default_rng(4), 1240, 376, 1500)
+    exp = ctx.calc_optical_flow_pyr_lk(a, b, pts)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    try:
+        for i in range(12):
+            ctx.set_stream((s1 if i % 2 else s2).cuda_stream)
+            got = ctx.calc_optical_flow_pyr_lk(a, b, pts) if i % 3 else ctx.calc_optical_flow_pyr_lk(b, a, pts)
+            if i % 3:
+                assert all(np.array_equal(x, y) for x, y in zip(got, exp)), i
+    finally:
+        ctx.set_stream(None)
+    assert all(np.array_equal(x, y) for x, y in zip(ctx.calc_optical_flow_pyr_lk(a, b, pts), exp))

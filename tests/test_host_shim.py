@@ -45,3 +45,28 @@ def test_init_frontend_matches_oracle(tmp_path):
     box = oracle.box_pyramid(a, 3)
     assert [int(v) for v in lines[1].split()] == [620, 188, 310, 94]
     assert [int(v) for v in lines[2].split()] == [int(box[1].sum()), int(box[2].sum())]
+
+    # The same call site with the reference's OWN types (cv::Mat, std::vector<cv::Point2f>, cv::TermCriteria ...) through
+    # include/dr3lk_opencv.hpp: the swap is a namespace change.  Built against tests/mock_opencv (no OpenCV headers in this
+    # image); its results must be the raw-pointer shim's, line for line.
+    exe2 = os.path.join(ROOT, "3dr_b200", "host", "opencv_callsite")
+    if not os.path.exists(exe2):
+        subprocess.run(["make", "-C", os.path.dirname(exe2), "opencv_callsite"], check=True)
+    r2 = subprocess.run([exe2, str(tmp_path / "a.pgm"), str(tmp_path / "b.pgm"), str(tmp_path / "pts.txt"), str(tmp_path / "out2.txt")],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, (r2.returncode, r2.stderr)
+    with open(tmp_path / "out2.txt") as f:
+        lines2 = f.read().split("\n")
+    assert lines2 == lines
+
+
+def test_default_context_device_selection(tmp_path):
+    """Context::thread_default() honours DR3LK_DEVICE; a device that does not exist is an error, not a silent fallback"""
+    exe = os.path.join(ROOT, "3dr_b200", "host", "init_frontend")
+    a = load_gray("kitti0.png")
+    _write_pgm(tmp_path / "a.pgm", a)
+    np.savetxt(tmp_path / "pts.txt", np.array([[100.0, 100.0]]), fmt="%.9g")
+    args = [exe, str(tmp_path / "a.pgm"), str(tmp_path / "a.pgm"), str(tmp_path / "pts.txt"), str(tmp_path / "o.txt")]
+    assert subprocess.run(args, env=dict(os.environ, DR3LK_DEVICE="0"), capture_output=True).returncode == 0
+    r = subprocess.run(args, env=dict(os.environ, DR3LK_DEVICE="4242"), capture_output=True, text=True)
+    assert r.returncode != 0
