@@ -14,6 +14,10 @@
 
 using namespace dr3lk;
 
+#ifndef DR3LK_TMA_DEFAULT
+#define DR3LK_TMA_DEFAULT 0
+#endif
+
 namespace {
 
 std::string g_create_error;
@@ -21,11 +25,14 @@ std::string g_create_error;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    // != 0: the buffer holds a derivative pyramid of this layout whose aprons are zero (kernels only ever write the interior
+    // of a level), so a pooled buffer that is reused for the same layout needs no clearing
+    unsigned long long zero_sig = 0;
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        p = nullptr; cap = 0; zero_sig = 0;
         // grow with slack so that slowly growing workloads do not reallocate every call
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -33,7 +40,7 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; zero_sig = 0; }
 };
 
 struct HostBuf {
@@ -137,6 +144,16 @@ struct dr3lk_ctx {
             }
         return DevBuf();
     }
+    // TMA descriptors already encoded for this context's buffers (key: address + geometry); encoding costs about a
+    // microsecond each, the single-call path would pay 12 of them per call
+    struct TmaKey {
+        const void* base;
+        unsigned long long dim[3], stride[2];
+        unsigned box[2];
+        int dtype;
+        bool operator==(const TmaKey& o) const { return memcmp(this, &o, sizeof(TmaKey)) == 0; }
+    };
+    std::vector<std::pair<TmaKey, CUtensorMap>> tma_cache;
     bool profiling = false;
     struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
     std::vector<Prof> prof;
@@ -271,6 +288,67 @@ void fill_lk_scalars(LKParams& lk, const LKArgs& a)
     lk.flags = a.flags;
 }
 
+// ---- TMA descriptors for the specialised LK kernels (cp.async.bulk.tensor staging) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tma_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// One rank-3 box descriptor over [batch][rows][pitch] elements of `esize` bytes starting at `base`; cached per context.
+bool tma_map(dr3lk_ctx* ctx, CUtensorMap* out, const void* base, int esize, unsigned long long pitch_elems, unsigned long long rows,
+             unsigned long long batch, unsigned long long img_stride_bytes, unsigned box_w, unsigned box_h)
+{
+    dr3lk_ctx::TmaKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.dim[0] = pitch_elems; k.dim[1] = rows; k.dim[2] = batch;
+    k.stride[0] = pitch_elems * esize; k.stride[1] = img_stride_bytes; k.box[0] = box_w; k.box[1] = box_h; k.dtype = esize;
+    for (auto& e : ctx->tma_cache)
+        if (e.first == k) { *out = e.second; return true; }
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {k.dim[0], k.dim[1], k.dim[2]};
+    const cuuint64_t gstr[2] = {k.stride[0], batch > 1 ? k.stride[1] : k.stride[0] * rows};
+    const cuuint32_t box[3] = {box_w, box_h, 1}, estr[3] = {1, 1, 1};
+    if (enc(out, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (ctx->tma_cache.size() >= 256) ctx->tma_cache.clear();
+    ctx->tma_cache.emplace_back(k, *out);
+    return true;
+}
+
+// Fills lk.tma[] for levels that carry the aprons (lk.fast_ok) and sets lk.use_tma.  Staging with TMA is opt-in / opt-out
+// through DR3LK_TMA (see DESIGN.md for the measurement behind the default).
+void fill_tma(dr3lk_ctx* ctx, LKParams& lk, int batch)
+{
+    static const int want = getenv("DR3LK_TMA") ? atoi(getenv("DR3LK_TMA")) : DR3LK_TMA_DEFAULT;
+    lk.use_tma = 0;
+    LkFastBoxes b;
+    if (!want || !lk.fast_ok || lk.max_level >= kTmaLevels || !lk_fast_boxes(lk.win_w, lk.win_h, &b)) return;
+    const int ax = kApronX, ay = apron_y(lk.win_h), dax = deriv_apron_x(lk.win_w);
+    for (int l = 0; l <= lk.max_level; l++) {
+        const LevelDesc& d = lk.lv[l];
+        const unsigned long long rows = (unsigned long long)d.h + 2 * ay;
+        if (!tma_map(ctx, &lk.tma[l].prev, d.prev - ((size_t)ay * d.pitch_p + ax), 1, d.pitch_p, rows, batch, d.prev_stride, b.i_w, b.i_h)) return;
+        if (!tma_map(ctx, &lk.tma[l].next, d.next - ((size_t)ay * d.pitch_n + ax), 1, d.pitch_n, rows, batch, d.next_stride, b.j_w, b.j_h)) return;
+        if (!tma_map(ctx, &lk.tma[l].deriv, d.deriv - ((size_t)ay * d.dpitch + dax), 4, d.dpitch, rows, batch, (unsigned long long)d.deriv_stride * 4,
+                     b.d_w, b.d_h))
+            return;
+    }
+    lk.use_tma = 1;
+}
+
 int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk, Workspace& W)
 {
     Launch L{stream, cudaSuccess, 0};
@@ -313,6 +391,7 @@ int run_tracking(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, LKParams& lk
         if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pair index kernel launch");
         lk.pair_idx = (const int*)W.pair_idx.p;
     }
+    fill_tma(ctx, lk, batch);
     return run_lk(ctx, stream, lk, W);
 }
 
@@ -947,21 +1026,27 @@ static void orphan_pyramids(dr3lk_ctx* ctx)
     ctx->live.clear();
 }
 
-// Enqueues the build of a pyramid object from a level-0 image that is already on the device (16-B pitched scratch,
-// pitch0 = align16(w)): apron copy (or plain copy for windows without aprons), Gaussian levels, derivatives.  No sync.
-static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_dev, cudaStream_t st, Launch& L)
+// Enqueues the build of a pyramid object from a level-0 image that is already on the device (rows `pitch0` bytes apart, any
+// alignment): apron copy (or plain copy for windows without aprons), Gaussian levels, derivatives.  No sync.
+static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_dev, size_t pitch0, cudaStream_t st, Launch& L)
 {
     const PyrLayout& P = p->P;
-    const int pitch0 = align_up(p->w, 16);
-    const size_t l0_bytes = (size_t)pitch0 * p->h;
+    const size_t l0_bytes = pitch0 * p->h;
     if (L.err != cudaSuccess) return;
     if (P.ax > 0) {
-        // level 0 is copied into its apron-carrying image; the derivative aprons are zeros
-        if (p->has_deriv) L.err = cudaMemsetAsync(p->deriv.p, 0, p->der_total * sizeof(int), st);
+        // level 0 is copied into its apron-carrying image; the derivative aprons are zeros: cleared once per (buffer, layout)
+        if (p->has_deriv) {
+            const unsigned long long sig = 1ull | ((unsigned long long)p->w << 1) ^ ((unsigned long long)p->h << 21) ^ ((unsigned long long)p->win_w << 41) ^
+                                           ((unsigned long long)p->win_h << 49) ^ ((unsigned long long)P.ml << 57);
+            if (p->deriv.zero_sig != sig) {
+                L.err = cudaMemsetAsync(p->deriv.p, 0, p->der_total * sizeof(int), st);
+                p->deriv.zero_sig = sig;
+            }
+        }
         launch_pad_level0(L, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
                           p->h, P.ax, P.ay, 1, 0);
     } else {
-        L.err = cudaMemcpyAsync(p->img.p, l0_dev, l0_bytes, cudaMemcpyDeviceToDevice, st);  // P.pitch[0] == pitch0 without aprons
+        L.err = cudaMemcpy2DAsync(p->img.p, P.pitch[0], l0_dev, pitch0, p->w, p->h, cudaMemcpyDeviceToDevice, st);
     }
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = p->lv[l];
@@ -1018,7 +1103,7 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
     Launch L{st, cudaSuccess, 0};
     L.err = cudaMemcpyAsync(ctx->ws.lvl0_prev.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);
-    pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, st, L);
+    pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, pitch0, st, L);
     // the pinned staging buffer is reused by the next call: wait for the upload
     if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st);
     if (L.err != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, L.err, "pyramid_create"); }
@@ -1138,7 +1223,7 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
     }
     Launch L{st, cudaSuccess, 0};
     L.err = cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st);
-    pyramid_enqueue(ctx, p2, dp, st, L);
+    pyramid_enqueue(ctx, p2, dp, pitch0, st, L);
     if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
     if (n > 0) {
         LKParams lk;

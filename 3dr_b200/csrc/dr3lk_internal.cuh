@@ -1,5 +1,6 @@
 // Internal declarations shared by the dr3lk CUDA translation units (sm_100a only).
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,8 +34,19 @@ struct LevelDesc {
     int w, h;
 };
 
+// TMA descriptors of one level for the specialised LK kernels: boxes of the template window (previous image, u8), of its
+// derivatives (int32 words) and of the search region (next image, u8) over the apron-carrying level allocations
+// [batch][rows + 2 * apron_y][pitch]; coordinate (0, 0) is the first apron byte.  Only the first kTmaLevels levels can be
+// described (kernel parameter space); deeper pyramids use the cp.async staging.
+constexpr int kTmaLevels = 6;   // keeps LKParams below the classic 4 KB kernel-parameter limit
+struct LevelTma {
+    CUtensorMap prev, deriv, next;
+};
+
 struct LKParams {
     LevelDesc lv[kMaxLevels];
+    LevelTma tma[kTmaLevels];
+    int use_tma;           // the descriptors above are valid: stage with cp.async.bulk.tensor instead of cp.async
     const float2* prev_pts;
     float2* next_pts;
     uint8_t* status;
@@ -107,6 +119,11 @@ void launch_pair_index(Launch& L, const int* pts_offset_dev, int batch, int n_to
 // lk_fast.cu -- returns false when the window size has no specialised kernel
 bool launch_lk_fast(Launch& L, const LKParams& p);
 bool lk_fast_supported(int win_w, int win_h);
+// TMA box shapes of the specialised kernel for this window: {template bytes, derivative ints, search bytes} x rows
+struct LkFastBoxes {
+    int i_w, i_h, d_w, d_h, j_w, j_h;
+};
+bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b);
 
 // ---- device helpers ----
 __device__ __forceinline__ int reflect101(int p, int len)

@@ -77,17 +77,22 @@ struct Geo {
     // Staging copies whole rounds of 32 lanes (no partial round, no idle-lane branch): regions are rounded up to whole
     // rounds of rows; the surplus rows are copied (the apron makes them addressable) and never read.
     static constexpr int J_ROWS = staged_rows(J_H, J_CH), I_ROWS = staged_rows(WH + 1, I_CH), D_ROWS = staged_rows(WH + 1, D_CH);
-    static constexpr int J_WORDS = J_PW * J_ROWS + 4;    // +4: realignment may read one word past the last row
-    static constexpr int I_WORDS = I_PW * I_ROWS + 4;
+    // region sizes in words, rounded to 128 bytes (TMA destinations must be 128-byte aligned)
+    static constexpr int J_WORDS = (J_PW * J_ROWS + 4 + 31) / 32 * 32;    // +4: realignment may read one word past the last row
+    static constexpr int I_WORDS = (I_PW * I_ROWS + 4 + 31) / 32 * 32;
     static constexpr int D_ZERO = D_PW * D_ROWS;         // two rows of zeros for runs that do not exist
-    static constexpr int D_WORDS = D_PW * (D_ROWS + 2) + 4;
+    static constexpr int D_WORDS = (D_PW * (D_ROWS + 2) + 4 + 31) / 32 * 32;
+    // TMA staging (cp.async.bulk.tensor): one box per region, exactly the rows that are read; the box rows land densely,
+    // which IS the padded layout above because every region is an odd number of 16-byte chunks wide
+    static_assert(J_PW == J_CH * 4 && I_PW == I_CH * 4 && D_PW == D_CH * 4, "TMA boxes need dense region rows");
+    static constexpr int TMA_I_BYTES = I_W * (WH + 1), TMA_D_BYTES = D_CH * 16 * (WH + 1), TMA_J_BYTES = J_W * J_H;
     static constexpr int PX = kApronX, PY = apron_y(WH), DPX = deriv_apron_x(WW);  // aprons of every level (bytes, rows, ints)
     static_assert(PY >= I_ROWS && PY >= D_ROWS && PY >= J_ROWS - 2 * MY, "apron rows must cover the rounded-up staging");
     // smallest level the kernel accepts: the aprons are filled by ONE reflection of the level
     static constexpr int MIN_H = PY + 1;
     static constexpr int MIN_W = PX + 1;
     static_assert(PX >= WW + 1 && PX % 16 == 0 && DPX >= WW + 1 && DPX % 4 == 0, "aprons must cover a window hanging over the border");
-    static constexpr int WARP_WORDS = (J_WORDS + I_WORDS + D_WORDS + 3) / 4 * 4;
+    static constexpr int WARP_WORDS = J_WORDS + I_WORDS + D_WORDS;
     static_assert((long long)NRUN * R * 8160LL * 4080LL < 2147483647LL, "per-lane int32 partial sums would overflow");
     static_assert(J_W >= WW + 1 + MX + MX + 15, "search region too narrow");
 };
@@ -178,6 +183,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA staging primitives (per-warp mbarriers: one elected lane arms the barrier and issues the boxes) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// one box of a rank-3 tensor [pair][row][column] at (x, y, pair) -> dense rows at dst (128-byte aligned)
+__device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* map, int x, int y, int pair, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(pair), "r"(smem_u32(bar)) : "memory");
+}
+
 template <typename G>
 struct Tracker {
     static constexpr int WW = G::WW, WH = G::WH;
@@ -208,11 +238,15 @@ struct Tracker {
     // x in [-PX, w + PX) and y in [-PY, h + PY) addressable.
     // Search region of the next image around window origin (inx, iny): J_W x J_H bytes from (rx0, ry0); window origins
     // rx0 .. rx0 + J_W - (WW+1), ry0 .. ry0 + 2*MY are inside it.
-    static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int h, int inx, int iny, int lane,
-                                                   int& rx0, int& ry0)
+    static __device__ __forceinline__ void origin_J(int pitch, int h, int inx, int iny, int& rx0, int& ry0)
     {
         rx0 = max(-G::PX, min((inx - G::MX) & ~15, pitch - G::PX - G::J_W));
         ry0 = max(-G::PY, min(iny - G::MY, h + G::PY - G::J_ROWS));
+    }
+    static __device__ __forceinline__ void stage_J(unsigned* sJ, const uint8_t* __restrict__ img, int pitch, int h, int inx, int iny, int lane,
+                                                   int& rx0, int& ry0)
+    {
+        origin_J(pitch, h, inx, iny, rx0, ry0);
         stage_rows<G::J_ROWS, G::J_CH, G::J_PW * 4>(sJ, lane, img + (ry0 * pitch + rx0), pitch);
     }
     // first staged column of the template window / its derivatives for window origin x = ipx
@@ -233,18 +267,31 @@ struct Tracker {
 
 // Persistent warps: every warp pulls the next feature index from a global counter until the batch is exhausted, so a
 // slow feature (many iterations) never holds other warps' slots.
-template <typename G>
+// TMA = true: the three regions are staged with cp.async.bulk.tensor boxes (one elected lane, completion on per-warp
+// mbarriers) instead of 11 - 13 cp.async rounds of all 32 lanes; same shared-memory layout, same arithmetic.
+template <typename G, bool TMA>
 __global__ void __launch_bounds__(G::WARPS * 32, G::MIN_BLOCKS)
 lk_fast_kernel(const __grid_constant__ LKParams P)
 {
     constexpr int WW = G::WW, WH = G::WH, R = G::R, NRUN = G::NRUN;
     using T = Tracker<G>;
-    extern __shared__ __align__(16) unsigned smem_u[];
+    extern __shared__ __align__(128) unsigned smem_u[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned* sJ = smem_u + warp * G::WARP_WORDS;
     unsigned* sI = sJ + G::J_WORDS;
     unsigned* sD = sI + G::I_WORDS;
+    // per-warp mbarriers behind the regions: [0] template window + derivatives, [1] search region; phase parities
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_u + G::WARPS * G::WARP_WORDS) + 2 * warp;
+    unsigned ph_t = 0, ph_j = 0;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(bars, 1);
+            mbar_init(bars + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     // ---- run geometry of this lane (constant for the whole kernel) ----
     int jofs[NRUN], iofs[NRUN], dofs[NRUN];
@@ -288,8 +335,25 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     auto issue_template = [&](int pair, const Origin& o, int level) {
         if (!o.inb) return;
         const LevelDesc& L = P.lv[level];
+        if (TMA) {
+            if (lane == 0) {
+                mbar_expect_tx(bars, G::TMA_I_BYTES + G::TMA_D_BYTES);
+                tma_box(sI, &P.tma[level].prev, T::x0_I(o.ipx, L.pitch_p) + G::PX, o.ipy + G::PY, pair, bars);
+                tma_box(sD, &P.tma[level].deriv, T::x0_D(o.ipx, L.dpitch) + G::DPX, o.ipy + G::PY, pair, bars);
+            }
+            return;
+        }
         T::stage_I(sI, L.prev + (unsigned long long)(unsigned)pair * L.prev_stride, L.pitch_p, o.ipx, o.ipy, lane);
         T::stage_D(sD, L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride, L.dpitch, o.ipx, o.ipy, lane);
+    };
+    // wait for the template window issued last (none is in flight when its origin was out of frame)
+    auto wait_template = [&](bool issued) {
+        if (TMA) {
+            if (issued) { mbar_wait(bars, ph_t); ph_t ^= 1; }
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
     };
     // Work distribution: every warp reserves P.fetch_n consecutive features with one atomic (1 for small batches, where
     // every resident warp should get its own feature; up to 8 for large ones: fewer atomics on the one counter)
@@ -311,7 +375,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     int pair = pair_of(f);
     Origin org = template_origin(pp, P.max_level);  // always the origin of the template window that is in flight / staged
     issue_template(pair, org, P.max_level);
-    cp_async_commit();
+    if (!TMA) cp_async_commit();
 
     for (;;) {
         // look ahead: the next feature's coarsest template window is prefetched while this one finishes
@@ -350,25 +414,41 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             // BOTH inside the staged region and inside the frame (OpenCV's bounds test), so one range test per axis
             // serves both; jb0 turns an origin into its byte offset in sJ.  Nothing staged: an empty range.
             int vx0 = 0x40000000, vy0 = 0x40000000, vxs = 0, vys = 0, jb0 = 0;
+            bool j_pending = false;  // TMA: a search-region box is in flight on bars[1]
             auto stage_search = [&](int ox, int oy) {
                 int rx0, ry0;
-                T::stage_J(sJ, imgJ, L.pitch_n, h, ox, oy, lane, rx0, ry0);
+                if (TMA) {
+                    T::origin_J(L.pitch_n, h, ox, oy, rx0, ry0);
+                    if (lane == 0) {
+                        mbar_expect_tx(bars + 1, G::TMA_J_BYTES);
+                        tma_box(sJ, &P.tma[level].next, rx0 + G::PX, ry0 + G::PY, pair, bars + 1);
+                    }
+                    j_pending = true;
+                } else {
+                    T::stage_J(sJ, imgJ, L.pitch_n, h, ox, oy, lane, rx0, ry0);
+                }
                 vx0 = max(rx0, -WW); vxs = min(rx0 + (G::J_W - (WW + 1)), w - 1) - vx0;
                 vy0 = max(ry0, -WH); vys = min(ry0 + 2 * G::MY, h - 1) - vy0;
                 jb0 = -(ry0 * (G::J_PW * 4) + rx0);
+            };
+            auto wait_search = [&]() {
+                if (TMA) {
+                    if (j_pending) { mbar_wait(bars + 1, ph_j); ph_j ^= 1; j_pending = false; }
+                } else {
+                    cp_async_wait<0>();
+                }
             };
             // Copy discipline: at most ONE cp.async group is in flight whenever the warp waits, and every wait is a
             // wait_group 0.  (An earlier version kept the template prefetch and the search region in flight together and
             // relied on wait_group 1 retiring them in issue order; under back-to-back levels -- zero iterations -- that
             // let a template phase start on a window that had not landed, about once in 10^5 features.)
-            cp_async_wait<0>();  // this level's template window (prefetched during the previous level) has landed
-            __syncwarp();
+            wait_template(inb);  // this level's template window (prefetched during the previous level) has landed
             // search region around the initial estimate: issued now, consumed after the template phase
             if (inb) {
                 const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
                 if ((unsigned)(jx + WW) < (unsigned)(w + WW) && (unsigned)(jy + WH) < (unsigned)(h + WH)) stage_search(jx, jy);
             }
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
 
             int dxr[NRUN][R], dyr[NRUN][R];
             int jinit[NRUN][R];  // 2^8 - 512 * I: the dp2a addend that turns the J sample into (J - I)
@@ -404,7 +484,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 }
             }
             // the search region has landed behind the template phase ...
-            cp_async_wait<0>();
+            wait_search();
             // ... and the template regions are free again: prefetch the next template window (next finer level of this
             // feature, or the coarsest level of the next feature) behind the iterations
             __syncwarp();
@@ -414,7 +494,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 org = template_origin(pq, level_q);
                 issue_template(pair_q, org, level_q);
             }
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
 
             if (!inb) {
                 if (level == 0) { status = 0; err = 0.f; }
@@ -456,8 +536,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     }
                     __syncwarp();
                     stage_search(inx, iny);
-                    cp_async_commit();
-                    cp_async_wait<0>();
+                    if (!TMA) cp_async_commit();
+                    wait_search();
                     __syncwarp();
                     jloaded = 0x7fffffff;
                 }
@@ -518,8 +598,8 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 if ((unsigned)(iqx - vx0) > (unsigned)vxs || (unsigned)(iqy - vy0) > (unsigned)vys) {
                     __syncwarp();
                     stage_search(iqx, iqy);
-                    cp_async_commit();
-                    cp_async_wait<0>();
+                    if (!TMA) cp_async_commit();
+                    wait_search();
                     __syncwarp();
                     jloaded = 0x7fffffff;
                 }
@@ -557,21 +637,19 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         if (f_next >= P.n_total) break;
         f = f_next; pp = pp_next; pair = pair_next;
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
 }
 
-template <typename G>
+template <typename G, bool TMA>
 bool launch_one(Launch& L, const LKParams& p)
 {
-    for (int l = 0; l <= p.max_level; l++)
-        if (p.lv[l].w < G::MIN_W || p.lv[l].h < G::MIN_H) return false;  // tiny level: lk_generic handles it
-    const size_t smem = (size_t)G::WARPS * G::WARP_WORDS * sizeof(unsigned);
-    L.err = cudaFuncSetAttribute(lk_fast_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)G::WARPS * G::WARP_WORDS * sizeof(unsigned) + (TMA ? G::WARPS * 16 : 0);
+    L.err = cudaFuncSetAttribute(lk_fast_kernel<G, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (L.err != cudaSuccess) return false;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_fast_kernel<G>, G::WARPS * 32, smem);
+    L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_fast_kernel<G, TMA>, G::WARPS * 32, smem);
     if (L.err != cudaSuccess) return false;
     const int want = (p.n_total + G::WARPS - 1) / G::WARPS;
     const int blocks = std::min(want, std::max(1, per_sm) * sms);
@@ -579,10 +657,24 @@ bool launch_one(Launch& L, const LKParams& p)
     static const int fetch_max = getenv("DR3LK_FETCH_MAX") ? atoi(getenv("DR3LK_FETCH_MAX")) : 8;
     // reserve several features per atomic only when every warp has at least 64 features to work through
     q.fetch_n = std::max(1, std::min(fetch_max, (int)(p.n_total / (64LL * blocks * G::WARPS))));
-    lk_fast_kernel<G><<<blocks, G::WARPS * 32, smem, L.stream>>>(q);
+    lk_fast_kernel<G, TMA><<<blocks, G::WARPS * 32, smem, L.stream>>>(q);
     L.err = cudaGetLastError();
     L.launches++;
     return L.err == cudaSuccess;  // true: the persistent kernel ran and consumed its work counter
+}
+
+template <typename G>
+bool launch_geo(Launch& L, const LKParams& p)
+{
+    for (int l = 0; l <= p.max_level; l++)
+        if (p.lv[l].w < G::MIN_W || p.lv[l].h < G::MIN_H) return false;  // tiny level: lk_generic handles it
+    return p.use_tma ? launch_one<G, true>(L, p) : launch_one<G, false>(L, p);
+}
+
+template <typename G>
+LkFastBoxes boxes_of()
+{
+    return LkFastBoxes{G::I_W, G::WH + 1, G::D_CH * 4, G::WH + 1, G::J_W, G::J_H};
 }
 
 }  // namespace
@@ -596,9 +688,16 @@ bool launch_lk_fast(Launch& L, const LKParams& p)
 {
     if (!lk_fast_supported(p.win_w, p.win_h) || !p.fast_ok) return false;
     if (L.err != cudaSuccess || p.n_total <= 0) return false;  // nothing launched; the generic launcher is a no-op here too
-    if (p.win_w == 21) return launch_one<Geo<21, 21, 7>>(L, p);
-    if (p.win_w == 31) return launch_one<Geo<31, 31, 8>>(L, p);
-    return launch_one<Geo<30, 30, 10>>(L, p);
+    if (p.win_w == 21) return launch_geo<Geo<21, 21, 7>>(L, p);
+    if (p.win_w == 31) return launch_geo<Geo<31, 31, 8>>(L, p);
+    return launch_geo<Geo<30, 30, 10>>(L, p);
+}
+
+bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b)
+{
+    if (!lk_fast_supported(win_w, win_h)) return false;
+    *b = win_w == 21 ? boxes_of<Geo<21, 21, 7>>() : (win_w == 31 ? boxes_of<Geo<31, 31, 8>>() : boxes_of<Geo<30, 30, 10>>());
+    return true;
 }
 
 }  // namespace dr3lk
