@@ -252,3 +252,46 @@ def test_c4_4k_31x31_five_levels_bit_exact(ctx):
     box = ctx.box_pyramid(a, 3)
     exp_box = oracle.box_pyramid(a, 3)
     assert all(np.array_equal(x, y) for x, y in zip(box[1:], exp_box[1:]))
+
+
+def test_lk_tma_staging_variant_is_bit_exact():
+    """DR3LK_TMA=1 selects the kernels that stage their three regions with cp.async.bulk.tensor boxes + per-warp mbarriers
+    instead of cp.async rounds (kept as a measured alternative, DESIGN.md: 201.2 vs 190.9 ms per C3 launch).  The switch is
+    read once per process, so the check runs in a child process: golden cases of all three specialised kernels, a ragged
+    batch, zero iterations and windows hanging over every border -- bit-exact against the oracle."""
+    import os
+    import subprocess
+    import sys
+    from _common import ROOT
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle
+from _common import golden_case, load_gray, random_points
+m = importlib.import_module("3dr_b200")
+def same(got, exp):
+    return all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(got, exp))
+with m.Context(0) as ctx:
+    for case in ("c1_default_21x21", "c1_31x31_L4", "c1_reference_30x30_initflow", "oddwidth_21x21"):
+        g = golden_case(case)
+        a, b = load_gray(g["prev"]), load_gray(g["next"])
+        args = (a, b, g["prev_pts"], g["init"], g["win"], g["max_level"], g["crit"], g["flags"])
+        assert same(ctx.calc_optical_flow_pyr_lk(*args), oracle.calc_optical_flow_pyr_lk(*args)), case
+    a, b = load_gray("kitti3.png"), load_gray("kitti4.png")
+    rng = np.random.default_rng(5)
+    pts = random_points(rng, a.shape[1], a.shape[0], 3000, margin=45)
+    for crit in ((3, 0, 0.01), (3, 30, 0.01)):
+        exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, (21, 21), 3, crit, 0)
+        for rep in range(20):
+            assert same(ctx.calc_optical_flow_pyr_lk(a, b, pts, None, (21, 21), 3, crit, 0), exp)
+    prev = np.stack([a, b, a]); nxt = np.stack([b, a, b])
+    offs = np.array([0, 700, 700, 3000], np.int32)
+    got = ctx.track_batch_host(prev, nxt, pts, offs)
+    for i in range(3):
+        sl = slice(offs[i], offs[i + 1])
+        po, so, eo = oracle.calc_optical_flow_pyr_lk(prev[i], nxt[i], pts[sl])
+        assert np.array_equal(got[1][sl], so) and np.array_equal(got[0][sl].view(np.uint32), po.view(np.uint32)) and np.array_equal(got[2][sl], eo)
+print("tma ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DR3LK_TMA="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "tma ok" in r.stdout, r.stderr[-3000:]
