@@ -34,7 +34,7 @@ SYMBOLS = [
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
     "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
     "dr3lk_multi_create", "dr3lk_multi_destroy", "dr3lk_multi_size", "dr3lk_multi_context", "dr3lk_multi_last_error", "dr3lk_shard_range",
-    "dr3lk_multi_track_batch_host",
+    "dr3lk_multi_track_batch_host", "dr3lk_init_first_frame", "dr3lk_init_second_frame", "dr3lk_init_score_fundamental",
 ]
 
 
@@ -112,6 +112,12 @@ def lib():
     L.dr3lk_fast_detect.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, P(c_int)]
     L.dr3lk_score_fundamental.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p, P(c_int)]
+    if hasattr(L, "dr3lk_init_first_frame"):  # absent only in older builds loaded through DR3LK_LIB for A/B runs
+        L.dr3lk_init_first_frame.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_int, c_double, c_int, c_void_p, c_int, c_int,
+                                             c_int, c_void_p, c_void_p, c_void_p, P(c_int), P(c_void_p)]
+        L.dr3lk_init_second_frame.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int] + lk_tail + [
+            c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_int)]
+        L.dr3lk_init_score_fundamental.argtypes = [c_void_p, c_void_p, c_int, ctypes.c_float, c_void_p, c_void_p, P(c_int)]
     _lib = L
     return L
 
@@ -364,6 +370,60 @@ class Context:
         best = ctypes.c_int(-1)
         self._check(lib().dr3lk_score_fundamental(self._h, F.ctypes.data, H, a.ctypes.data, b.ctypes.data, n, float(sigma), sc.ctypes.data,
                                                   inl.ctypes.data if want_inliers else None, ctypes.byref(best)))
+        return sc, inl, best.value
+
+    # ---- the two-frame initialiser front end, device-resident between its steps (src/initialization.cpp:546-661) ----
+    def init_first_frame(self, img, n_levels=3, cell_size=30, fast_threshold=20, detection_threshold=20.0, occupancy=None,
+                         box_mode=BOX_AUTO_X86, win=(30, 30), max_level=4):
+        """Init::process_first_frame: one upload; FastDetector::detect on the Frame's box pyramid AND the frame's LK pyramid.
+        Returns (xy, level, score, Pyramid)."""
+        img0 = np.ascontiguousarray(_gray(img))
+        h, w = img0.shape
+        ncell = (-(-w // cell_size)) * (-(-h // cell_size))
+        xy, lv, sc = np.zeros((ncell, 2), np.int32), np.zeros(ncell, np.int32), np.zeros(ncell, np.float32)
+        occ = np.ascontiguousarray(occupancy, np.uint8) if occupancy is not None else None
+        n, out = ctypes.c_int(0), ctypes.c_void_p()
+        self._check(lib().dr3lk_init_first_frame(self._h, img0.ctypes.data, w, h, img0.strides[0], n_levels, cell_size, fast_threshold,
+                                                 float(detection_threshold), box_mode, occ.ctypes.data if occ is not None else None,
+                                                 win[0], win[1], max_level, xy.ctypes.data, lv.ctypes.data, sc.ctypes.data, ctypes.byref(n),
+                                                 ctypes.byref(out)))
+        return xy[:n.value].copy(), lv[:n.value].copy(), sc[:n.value].copy(), Pyramid._wrap(self, out, win, (h, w))
+
+    def init_second_frame(self, ref_pyr, cur_img, kps_ref, kps_cur=None, max_level=4, criteria=(TERM_COUNT | TERM_EPS, 1000, 1e-3),
+                          flags=USE_INITIAL_FLOW, min_eig_threshold=1e-4, fx=None, fy=None, cx=0.0, cy=0.0, dist=None):
+        """Init::process_second_frame up to the RANSAC: one upload, LK against the reference pyramid, erase-by-status, disparities,
+        bearings; one download.  Defaults are the reference's literal parameters (src/initialization.cpp:593-613).
+        Returns dict(ref, cur, disparity, bearing, status, err)."""
+        img1 = _gray(cur_img)
+        if img1.shape != ref_pyr.shape:
+            raise Dr3lkError(E_SIZE, "(-215:Assertion failed) prevImg.size() == nextImg.size()")
+        r = np.ascontiguousarray(np.asarray(kps_ref, np.float32).reshape(-1, 2))
+        n = r.shape[0]
+        c = np.ascontiguousarray(np.asarray(kps_cur, np.float32).reshape(-1, 2)) if kps_cur is not None else None
+        o_r, o_c = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32)
+        disp = np.zeros(n, np.float64)
+        bear = np.zeros((n, 3), np.float64) if fx is not None else None
+        st, err = np.zeros(n, np.uint8), np.zeros(n, np.float32)
+        d5 = np.ascontiguousarray(dist, np.float64) if dist is not None else None
+        k = ctypes.c_int(0)
+        win = ref_pyr.win
+        self._check(lib().dr3lk_init_second_frame(
+            self._h, ref_pyr._h, img1.ctypes.data, img1.strides[0], r.ctypes.data, c.ctypes.data if c is not None else None, n, win[0], win[1],
+            max_level, criteria[0], criteria[1], float(criteria[2]), flags, float(min_eig_threshold), float(fx or 0.0), float(fy or 0.0),
+            float(cx), float(cy), d5.ctypes.data if d5 is not None else None, o_r.ctypes.data, o_c.ctypes.data, disp.ctypes.data,
+            bear.ctypes.data if bear is not None else None, st.ctypes.data, err.ctypes.data, ctypes.byref(k)))
+        k = k.value
+        return {"ref": o_r[:k], "cur": o_c[:k], "disparity": disp[:k], "bearing": bear[:k] if bear is not None else None, "status": st, "err": err}
+
+    def init_score_fundamental(self, F21, n_kept, sigma=1.0, want_inliers=True):
+        """CheckFundamental for a batch of hypotheses against the tracks the last init_second_frame left on the device."""
+        F = np.ascontiguousarray(np.asarray(F21, np.float32).reshape(-1, 9))
+        H = F.shape[0]
+        sc = np.zeros(H, np.float32)
+        inl = np.zeros((H, n_kept), np.uint8) if want_inliers else None
+        best = ctypes.c_int(-1)
+        self._check(lib().dr3lk_init_score_fundamental(self._h, F.ctypes.data, H, float(sigma), sc.ctypes.data,
+                                                       inl.ctypes.data if want_inliers else None, ctypes.byref(best)))
         return sc, inl, best.value
 
     def track_batch(self, prev_ptr, next_ptr, w, h, pitch, image_stride, batch, prev_pts_ptr, next_pts_ptr, status_ptr,

@@ -154,12 +154,21 @@ struct dr3lk_ctx {
         bool operator==(const TmaKey& o) const { return memcmp(this, &o, sizeof(TmaKey)) == 0; }
     };
     std::vector<std::pair<TmaKey, CUtensorMap>> tma_cache;
+    // compacted (ref, cur) points of the last dr3lk_init_second_frame, kept on the device for dr3lk_init_score_fundamental
+    DevBuf tracks;
+    int n_tracks = 0;
+    size_t tracks_cur_offset = 0;  // byte offset of the compacted current points inside `tracks`
     bool profiling = false;
     struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
     std::vector<Prof> prof;
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 6;   // capacity; dr3lk_track_batch_host uses n_slots() of them (3 unless DR3LK_SLOTS says otherwise)
     Workspace slot_ws[kSlots];    // chunk pipeline of dr3lk_track_batch_host
-    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    static int n_slots()
+    {
+        static const int n = getenv("DR3LK_SLOTS") ? std::min(kSlots, std::max(1, atoi(getenv("DR3LK_SLOTS")))) : 3;  // tuning knob
+        return n;
+    }
 };
 
 namespace {
@@ -469,6 +478,7 @@ void dr3lk_destroy(dr3lk_ctx* ctx)
     orphan_pyramids(ctx);
     ctx->ws.release();
     ctx->pinned.release();
+    ctx->tracks.release();
     for (auto& b : ctx->pool) b.release();
     for (int i = 0; i < dr3lk_ctx::kSlots; i++) {
         ctx->slot_ws[i].release();
@@ -720,16 +730,17 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     CU_TRY(ctx, ctx->pinned.reserve(total));
     uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    for (int y = 0; y < h; y++) {
-        memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
-        memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
-    }
+    // The previous image crosses PCIe while the host is still packing the next one: two copies, the first one hidden behind
+    // the second memcpy (the staging memcpy of ~0.5 MB per image is as long as its DMA)
+    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, img_bytes, cudaMemcpyHostToDevice, st));
+    for (int y = 0; y < h; y++) memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
     memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
     const int offs[2] = {0, n};
     memcpy(hp + o_offs, offs, sizeof(offs));
     size_t in_bytes = o_next;
     if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
-    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, hp + img_bytes, in_bytes - img_bytes, cudaMemcpyHostToDevice, st));
     rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(dp + o_prev), (float*)(dp + o_next),
                             dp + o_status, err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
     if (rc != DR3LK_OK) return rc;
@@ -757,7 +768,8 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     if (pts_offset[batch] == 0) return DR3LK_OK;
     if (!prev_pts || !next_pts || !status) return fail(ctx, DR3LK_E_ARG, "track_batch_host: null point / status buffer");
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < dr3lk_ctx::kSlots; i++)
+    const int n_slots = dr3lk_ctx::n_slots();
+    for (int i = 0; i < n_slots; i++)
         if (!ctx->slot_stream[i]) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
     // Whatever way this function returns, no copy may still be in flight: earlier chunks read `offs_host` (a local) and write
     // the caller's output buffers.  The guard drains the slot streams on every exit, error returns included.
@@ -769,7 +781,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
     cudaEvent_t ev_start;
     CU_TRY(ctx, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     CU_TRY(ctx, cudaEventRecord(ev_start, ctx->stream));
-    for (int i = 0; i < dr3lk_ctx::kSlots; i++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ev_start, 0));
+    for (int i = 0; i < n_slots; i++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ev_start, 0));
     cudaEventDestroy(ev_start);
 
     // Chunk boundaries.  chunk_pairs > 0: equal chunks of that many pairs.  0 = choose: ~128 MB of level-0 pixels per
@@ -781,7 +793,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         const size_t per_pair = 2 * (size_t)w * h;
         static const size_t chunk_mb = getenv("DR3LK_CHUNK_MB") ? (size_t)atoi(getenv("DR3LK_CHUNK_MB")) : 128;  // tuning knob
         int full = (int)std::max<size_t>(1, (chunk_mb << 20) / per_pair);
-        full = std::min(full, std::max(1, (batch + 2 * dr3lk_ctx::kSlots - 1) / (2 * dr3lk_ctx::kSlots)));
+        full = std::min(full, std::max(1, (batch + 2 * n_slots - 1) / (2 * n_slots)));
         int next = std::max(1, full / 16);
         while (cb.back() < batch) {
             cb.push_back(std::min(batch, cb.back() + next));
@@ -800,7 +812,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         for (int b = b0; b <= b1; b++) offs_host.push_back(pts_offset[b] - pts_offset[b0]);
     }
     for (int c = 0; c < n_chunks; c++) {
-        const int slot = c % dr3lk_ctx::kSlots;
+        const int slot = c % n_slots;
         Workspace& W = ctx->slot_ws[slot];
         cudaStream_t st = ctx->slot_stream[slot];
         const int b0 = cb[c], b1 = cb[c + 1], nb = b1 - b0;
@@ -831,7 +843,7 @@ int dr3lk_track_batch_host(dr3lk_ctx* ctx, const uint8_t* prev, const uint8_t* n
         if (stats) CU_TRY(ctx, cudaMemcpyAsync(stats + p0, dp + o_stats, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
     // ... and the context stream continues after them, so events on it bracket the whole call
-    for (int i = 0; i < dr3lk_ctx::kSlots; i++) {
+    for (int i = 0; i < n_slots; i++) {
         cudaEvent_t ev;
         CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU_TRY(ctx, cudaEventRecord(ev, ctx->slot_stream[i]));
@@ -1304,9 +1316,11 @@ int dr3lk_filter_tracks(dr3lk_ctx* ctx, const float* ref_pts, const float* cur_p
 /* f-1: FAST-10 + grid Shi-Tomasi selection                                                        */
 /* ---------------------------------------------------------------------------------------------- */
 
-int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size, int fast_threshold,
-                      double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score,
-                      int* n_out)
+// FastDetector::detect on one upload of the image; lk_win_w > 0: the LK pyramid (Gaussian levels + Scharr derivatives) of
+// the same device copy is built behind it and returned in *lk_pyr (dr3lk_init_first_frame).
+static int fast_detect_impl(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size, int fast_threshold,
+                            double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score,
+                            int* n_out, int lk_win_w, int lk_win_h, int lk_max_level, dr3lk_pyramid** lk_pyr)
 {
     if (!ctx) return DR3LK_E_ARG;
     if (!img || !out_xy || !out_level || !out_score || !n_out || step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "fast_detect: bad argument");
@@ -1367,10 +1381,20 @@ int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t s
     launch_fast_gather(L, (const unsigned long long*)(dp + o_keys), ncell, (const int*)(dp + o_lw), (int*)(dp + o_xy), (int*)(dp + o_lv),
                        (float*)(dp + o_sc), (int*)(dp + o_cnt));
     ctx->launches += L.launches;
+    L.launches = 0;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "fast_detect kernel launch");
+    dr3lk_pyramid* pyr = nullptr;
+    if (lk_pyr) {
+        int rc = pyramid_alloc(ctx, w, h, lk_win_w, lk_win_h, lk_max_level, true, &pyr);
+        if (rc != DR3LK_OK) { cudaStreamSynchronize(st); return rc; }
+        pyramid_enqueue(ctx, pyr, dp + off[0], (size_t)w, st, L);  // the level-0 copy FAST just read: no second upload
+        if (L.err != cudaSuccess) { cudaStreamSynchronize(st); pyramid_free(pyr, false); return fail_cuda(ctx, L.err, "init_first_frame: LK pyramid"); }
+    }
     uint8_t* h_out = (uint8_t*)h_lw + 32;
-    CU_TRY(ctx, cudaMemcpyAsync(h_out, dp + o_xy, dev_total - o_xy, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    cudaError_t ce = cudaMemcpyAsync(h_out, dp + o_xy, dev_total - o_xy, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { if (pyr) pyramid_free(pyr, false); return fail_cuda(ctx, ce, "fast_detect: download"); }
+    if (lk_pyr) *lk_pyr = pyr;
     const int n = *reinterpret_cast<const int*>(h_out + (o_cnt - o_xy));
     *n_out = n;
     memcpy(out_xy, h_out, 8 * (size_t)n);
@@ -1379,19 +1403,137 @@ int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t s
     return DR3LK_OK;
 }
 
+int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size, int fast_threshold,
+                      double detection_threshold, int box_mode, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score,
+                      int* n_out)
+{
+    return fast_detect_impl(ctx, img, w, h, step, n_levels, cell_size, fast_threshold, detection_threshold, box_mode, occupancy, out_xy,
+                            out_level, out_score, n_out, 0, 0, 0, nullptr);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* the two-frame initialiser front end, device-resident between its steps                          */
+/* ---------------------------------------------------------------------------------------------- */
+
+int dr3lk_init_first_frame(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size, int fast_threshold,
+                           double detection_threshold, int box_mode, const uint8_t* occupancy, int win_w, int win_h, int max_level,
+                           int* out_xy, int* out_level, float* out_score, int* n_out, dr3lk_pyramid** ref_pyramid)
+{
+    if (!ctx || !ref_pyramid) return DR3LK_E_ARG;
+    *ref_pyramid = nullptr;
+    LKArgs a{win_w, win_h, max_level, 0, 0, 0, 0., 0.};
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    return fast_detect_impl(ctx, img, w, h, step, n_levels, cell_size, fast_threshold, detection_threshold, box_mode, occupancy, out_xy,
+                            out_level, out_score, n_out, win_w, win_h, max_level, ref_pyramid);
+}
+
+int dr3lk_init_second_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* ref, const uint8_t* cur_img, size_t cur_step, const float* kps_ref,
+                            const float* kps_cur, int n, int win_w, int win_h, int max_level, int crit_type, int crit_max_count,
+                            double crit_eps, int flags, double min_eig_threshold, double fx, double fy, double cx, double cy,
+                            const double* distortion, float* out_ref, float* out_cur, double* out_disparity, double* out_bearing,
+                            uint8_t* out_status, float* out_err, int* n_kept)
+{
+    if (!ctx || !ref) return DR3LK_E_ARG;
+    if (!n_kept) return fail(ctx, DR3LK_E_ARG, "init_second_frame: n_kept is null");
+    *n_kept = 0;
+    ctx->n_tracks = 0;
+    LKArgs a{win_w, win_h, max_level, crit_type, crit_max_count, flags, crit_eps, min_eig_threshold};
+    const int w = ref->w, h = ref->h;
+    int rc = check_lk_args(ctx, w, h, a);
+    if (rc != DR3LK_OK) return rc;
+    if (ref->ctx != ctx) return fail(ctx, DR3LK_E_ARG, "the pyramid belongs to another context");
+    if (ref->win_w != win_w || ref->win_h != win_h) return fail(ctx, DR3LK_E_ARG, "the pyramid was built for another window size");
+    if (!ref->has_deriv) return fail(ctx, DR3LK_E_ARG, "the reference pyramid was built without derivatives");
+    if (!cur_img || cur_step < (size_t)w) return fail(ctx, DR3LK_E_ARG, "init_second_frame: bad image arguments");
+    if (n < 0) return fail(ctx, DR3LK_E_ARG, "negative point count");
+    if (n == 0) return DR3LK_OK;
+    if (!kps_ref || !out_ref || !out_cur || !out_disparity) return fail(ctx, DR3LK_E_ARG, "init_second_frame: null buffer");
+    if ((flags & DR3LK_USE_INITIAL_FLOW) && !kps_cur) return fail(ctx, DR3LK_E_ARG, "OPTFLOW_USE_INITIAL_FLOW needs kps_cur");
+    if (out_bearing && (fx == 0.0 || fy == 0.0)) return fail(ctx, DR3LK_E_ARG, "init_second_frame: zero focal length");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Workspace& W = ctx->ws;
+    dr3lk_pyramid* p2 = nullptr;
+    rc = pyramid_alloc(ctx, w, h, win_w, win_h, max_level, false, &p2);
+    if (rc != DR3LK_OK) return rc;
+    // ONE upload: [new image][kps_ref 8n][offsets 16][kps_cur 8n]; device-only behind it: [err 4n][status n]
+    const int pitch0 = align_up(w, 16);
+    const size_t img_block = align_up_sz((size_t)pitch0 * h, 256);
+    const size_t n8 = align_up_sz(8 * (size_t)n, 16), n4 = align_up_sz(4 * (size_t)n, 16), n1 = align_up_sz((size_t)n, 16), n24 = align_up_sz(24 * (size_t)n, 16);
+    const size_t o_prev = img_block, o_offs = o_prev + n8, o_next = o_offs + 16, o_err = o_next + n8, o_status = o_err + n4, in_total = o_status + n1;
+    // ONE download, from the resident track block: [out_ref 8n][out_cur 8n][disp 8n][bearing 24n][count 16][status n][err 4n]
+    const size_t t_ref = 0, t_cur = n8, t_disp = 2 * n8, t_bear = 3 * n8, t_cnt = t_bear + n24, t_status = t_cnt + 16, t_err = t_status + n1,
+                 t_total = t_err + n4;
+    cudaError_t e = W.lvl0_prev.reserve(in_total);
+    if (e == cudaSuccess) e = ctx->tracks.reserve(t_total);
+    if (e == cudaSuccess) e = ctx->pinned.reserve(std::max(in_total, t_total));
+    if (e != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, e, "init_second_frame: allocation"); }
+    uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
+    uint8_t* tp = (uint8_t*)ctx->tracks.p;
+    uint8_t* hp = (uint8_t*)ctx->pinned.p;
+    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, cur_img + (size_t)y * cur_step, (size_t)w);
+    const int offs[2] = {0, n};
+    memcpy(hp + o_prev, kps_ref, 8 * (size_t)n);
+    memcpy(hp + o_offs, offs, sizeof(offs));
+    size_t in_bytes = o_next;
+    if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, kps_cur, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
+    Launch L{st, cudaSuccess, 0};
+    L.err = cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st);
+    pyramid_enqueue(ctx, p2, dp, pitch0, st, L);
+    if (L.err != cudaSuccess) { cudaStreamSynchronize(st); pyramid_free(p2, false); return fail_cuda(ctx, L.err, "init_second_frame: pyramid of the new frame"); }
+    LKParams lk;
+    memset(&lk, 0, sizeof(lk));
+    const int ml = std::min(std::min(ref->P.ml, p2->P.ml), max_level);
+    for (int l = 0; l <= ml; l++) {
+        lk.lv[l] = ref->lv[l];
+        lk.lv[l].next = p2->lv[l].prev;
+        lk.lv[l].pitch_n = p2->lv[l].pitch_p;
+        lk.lv[l].next_stride = p2->lv[l].prev_stride;
+    }
+    lk.max_level = ml;
+    lk.fast_ok = ref->P.ax > 0;
+    // status / err go straight into the track block so that everything comes back in one copy
+    rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), tp + t_status, (float*)(tp + t_err), offs,
+                      (const int*)(dp + o_offs), n, nullptr, a);
+    if (rc != DR3LK_OK) { cudaStreamSynchronize(st); pyramid_free(p2, false); return rc; }
+    // src/initialization.cpp:615-635 on the device: erase !status (order kept), disparity, cam2world of the current point
+    launch_filter_tracks(L, (const float*)(dp + o_prev), (const float*)(dp + o_next), tp + t_status, n, fx != 0.0 ? fx : 1.0, fy != 0.0 ? fy : 1.0,
+                         cx, cy, distortion, (float*)(tp + t_ref), (float*)(tp + t_cur), (double*)(tp + t_disp),
+                         out_bearing ? (double*)(tp + t_bear) : nullptr, (int*)(tp + t_cnt));
+    ctx->launches += L.launches;
+    if (L.err == cudaSuccess) L.err = cudaMemcpyAsync(hp, tp, t_total, cudaMemcpyDeviceToHost, st);
+    if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st); else cudaStreamSynchronize(st);
+    pyramid_free(p2, true);
+    if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "init_second_frame");
+    const int k = *reinterpret_cast<const int*>(hp + t_cnt);
+    *n_kept = k;
+    ctx->n_tracks = k;
+    ctx->tracks_cur_offset = t_cur;
+    memcpy(out_ref, hp + t_ref, 8 * (size_t)k);
+    memcpy(out_cur, hp + t_cur, 8 * (size_t)k);
+    memcpy(out_disparity, hp + t_disp, 8 * (size_t)k);
+    if (out_bearing) memcpy(out_bearing, hp + t_bear, 24 * (size_t)k);
+    if (out_status) memcpy(out_status, hp + t_status, (size_t)n);
+    if (out_err) memcpy(out_err, hp + t_err, 4 * (size_t)n);
+    return DR3LK_OK;
+}
+
 
 /* ---------------------------------------------------------------------------------------------- */
 /* f-4: RANSAC fundamental-matrix hypothesis scoring                                               */
 /* ---------------------------------------------------------------------------------------------- */
 
-int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, int n, float sigma,
-                            float* out_scores, uint8_t* out_inliers, int* best)
+// dev1 / dev2 != nullptr: the matched points are already on the device (dr3lk_init_score_fundamental), only F goes up
+static int score_fundamental_impl(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, const float* dev1,
+                                  const float* dev2, int n, float sigma, float* out_scores, uint8_t* out_inliers, int* best)
 {
     if (!ctx) return DR3LK_E_ARG;
     if (n_hyp < 0 || n < 0 || !best) return fail(ctx, DR3LK_E_ARG, "score_fundamental: bad argument");
     *best = -1;
     if (n_hyp == 0) return DR3LK_OK;
-    if (!F21 || !out_scores || (n > 0 && (!pts1 || !pts2)) || !(sigma > 0.f)) return fail(ctx, DR3LK_E_ARG, "score_fundamental: bad argument");
+    const bool resident = dev1 != nullptr;
+    if (!F21 || !out_scores || (n > 0 && !resident && (!pts1 || !pts2)) || !(sigma > 0.f)) return fail(ctx, DR3LK_E_ARG, "score_fundamental: bad argument");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     Workspace& W = ctx->ws;
@@ -1403,12 +1545,12 @@ int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const f
     uint8_t* dp = (uint8_t*)W.pts.p;
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     memcpy(hp + i_F, F21, 36 * (size_t)n_hyp);
-    if (n > 0) { memcpy(hp + i_p1, pts1, 8 * (size_t)n); memcpy(hp + i_p2, pts2, 8 * (size_t)n); }
-    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, o_s, cudaMemcpyHostToDevice, st));
+    if (n > 0 && !resident) { memcpy(hp + i_p1, pts1, 8 * (size_t)n); memcpy(hp + i_p2, pts2, 8 * (size_t)n); }
+    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, resident ? bF : o_s, cudaMemcpyHostToDevice, st));
     Launch L{st, cudaSuccess, 0};
     // const float invSigmaSquare = 1.0/(sigma*sigma): float product, double division, rounded to float
     const float inv_sigma2 = (float)(1.0 / (double)(sigma * sigma));
-    launch_score_fundamental(L, (const float*)(dp + i_F), n_hyp, (const float*)(dp + i_p1), (const float*)(dp + i_p2), n, inv_sigma2,
+    launch_score_fundamental(L, (const float*)(dp + i_F), n_hyp, resident ? dev1 : (const float*)(dp + i_p1), resident ? dev2 : (const float*)(dp + i_p2), n, inv_sigma2,
                              (float*)(dp + o_s), out_inliers ? dp + o_i : nullptr);
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "score_fundamental kernel launch");
@@ -1421,6 +1563,22 @@ int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const f
     for (int i = 0; i < n_hyp; i++)
         if (out_scores[i] > bs) { bs = out_scores[i]; *best = i; }
     return DR3LK_OK;
+}
+
+int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, int n, float sigma,
+                            float* out_scores, uint8_t* out_inliers, int* best)
+{
+    return score_fundamental_impl(ctx, F21, n_hyp, pts1, pts2, nullptr, nullptr, n, sigma, out_scores, out_inliers, best);
+}
+
+int dr3lk_init_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, float sigma, float* out_scores, uint8_t* out_inliers, int* best)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (ctx->n_tracks <= 0 || !ctx->tracks.p) return fail(ctx, DR3LK_E_ARG, "init_score_fundamental: no tracks resident (call dr3lk_init_second_frame first)");
+    // layout of the resident block: [out_ref 8n'][out_cur 8n'] with n' = the point count of the second-frame call
+    const float* d1 = (const float*)ctx->tracks.p;
+    const float* d2 = (const float*)((const uint8_t*)ctx->tracks.p + ctx->tracks_cur_offset);
+    return score_fundamental_impl(ctx, F21, n_hyp, nullptr, nullptr, d1, d2, ctx->n_tracks, sigma, out_scores, out_inliers, best);
 }
 
 }  // extern "C"

@@ -209,6 +209,35 @@ int dr3lk_fast_detect(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t s
 int dr3lk_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, const float* pts1, const float* pts2, int n, float sigma,
                             float* out_scores, uint8_t* out_inliers, int* best);
 
+/* ---- the two-frame initialiser front end in three calls, device-resident between its steps ------------------------
+ * reference: init::Init::process_first_frame / process_second_frame, src/initialization.cpp:546-661.  The four f-rows above
+ * as separate host-buffer calls cost four uploads / downloads / synchronisations per frame pair; these three entry points
+ * chain them on the device and return bit-identical results.
+ *
+ * dr3lk_init_first_frame (src/initialization.cpp:546-585 + src/frame.cpp:13-20): ONE upload of the image; the Frame's box
+ * pyramid and FastDetector::detect on it (arguments and outputs of dr3lk_fast_detect) AND, from the same device copy, the LK
+ * pyramid of the frame for the tracking calls that follow (as dr3lk_pyramid_create with win / max_level); ONE download.
+ *
+ * dr3lk_init_second_frame (src/initialization.cpp:587-657): ONE upload (new image, kps_ref, kps_cur), the new frame's Gaussian
+ * pyramid, cv::calcOpticalFlowPyrLK against the reference pyramid (arguments of dr3lk_track_frame), then the erase-by-status
+ * loop, disparities and cam2world bearings of lines 615-635 (arguments and outputs of dr3lk_filter_tracks); ONE download.
+ * out_status / out_err (n entries each, may be NULL) are the raw LK outputs.  The compacted (ref, cur) points stay on the device.
+ *
+ * dr3lk_init_score_fundamental (src/initialization.cpp:81-133, 171-249): scores hypotheses against the points the last
+ * dr3lk_init_second_frame left on the device -- only the matrices go up, the scores (and inlier masks, n_hyp x n_kept bytes or
+ * NULL) come back.  Results as dr3lk_score_fundamental on the compacted points. */
+int dr3lk_init_first_frame(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int n_levels, int cell_size,
+                           int fast_threshold, double detection_threshold, int box_mode, const uint8_t* occupancy, int win_w,
+                           int win_h, int max_level, int* out_xy, int* out_level, float* out_score, int* n_out,
+                           dr3lk_pyramid** ref_pyramid);
+int dr3lk_init_second_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* ref, const uint8_t* cur_img, size_t cur_step, const float* kps_ref,
+                            const float* kps_cur, int n, int win_w, int win_h, int max_level, int crit_type, int crit_max_count,
+                            double crit_eps, int flags, double min_eig_threshold, double fx, double fy, double cx, double cy,
+                            const double* distortion, float* out_ref, float* out_cur, double* out_disparity, double* out_bearing,
+                            uint8_t* out_status, float* out_err, int* n_kept);
+int dr3lk_init_score_fundamental(dr3lk_ctx* ctx, const float* F21, int n_hyp, float sigma, float* out_scores, uint8_t* out_inliers,
+                                 int* best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,16 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("C3") and d["config"]["corners_per_pair"] == 8192 and d["config"]["pairs_per_gpu"] == 4096
+    # both arms print the SAME config dict (the driver compares them): the keys our arm prints are exactly these
+    assert sorted(d["config"]) == ["corners_per_pair", "distinct_pairs_per_gpu", "l2", "max_level", "pairs_per_gpu", "sharding", "win", "workload"]
+    assert "larger than L2" in d["config"]["l2"] and d["cpu_sample_pairs_per_step"] == 2
+
+
+def test_our_arm_builds_the_same_config_dict():
+    """static check (no GPU here): our arm emits `cfg` itself as "config" -- nothing is merged into it after the reference
+    arm's copy was built"""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": cfg') >= 3 and "dict(cfg," not in src and 'cfg["cpu_affinity"]' not in src
 
 
 def test_reference_arm_other_ranks_stay_silent():
