@@ -126,6 +126,16 @@ struct LkFastBoxes {
 bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b);
 
 // ---- device helpers ----
+// A NaN coordinate: x86 OpenCV's cvFloor turns it into INT_MIN (cvttss2si's "integer indefinite"), which fails every bounds
+// test, so the point is reported lost.  F2I on the GPU returns 0 for NaN, which would pass them -- map NaN to a huge
+// negative coordinate once, when the point is loaded (infinities and huge values already saturate F2I and fail the tests).
+__device__ __forceinline__ float2 sanitize_point(float2 p)
+{
+    if (!(p.x == p.x)) p.x = -1e30f;
+    if (!(p.y == p.y)) p.y = -1e30f;
+    return p;
+}
+
 __device__ __forceinline__ int reflect101(int p, int len)
 {
     if ((unsigned)p < (unsigned)len) return p;

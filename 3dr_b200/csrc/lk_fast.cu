@@ -371,7 +371,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     if (blockIdx.x == 0 && threadIdx.x == 0) P.work_counter[(P.work_epoch & 1) ^ 1] = 0;  // ready for the next launch
     int f = fetch();
     if (f >= P.n_total) return;
-    float2 pp = P.prev_pts[f];
+    float2 pp = sanitize_point(P.prev_pts[f]);
     int pair = pair_of(f);
     Origin org = template_origin(pp, P.max_level);  // always the origin of the template window that is in flight / staged
     issue_template(pair, org, P.max_level);
@@ -382,10 +382,10 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         const int f_next = fetch();
         float2 pp_next = make_float2(0.f, 0.f);
         int pair_next = 0;
-        if (f_next < P.n_total) { pp_next = P.prev_pts[f_next]; pair_next = pair_of(f_next); }
+        if (f_next < P.n_total) { pp_next = sanitize_point(P.prev_pts[f_next]); pair_next = pair_of(f_next); }
 
         float2 np = make_float2(0.f, 0.f);
-        if (P.flags & DR3LK_USE_INITIAL_FLOW) np = P.next_pts[f];
+        if (P.flags & DR3LK_USE_INITIAL_FLOW) np = sanitize_point(P.next_pts[f]);
 
         int status = 1;
         float err = 0.f;

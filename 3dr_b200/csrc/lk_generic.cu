@@ -85,9 +85,9 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
     // which frame pair does this feature belong to?
     const int pair = P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f);
 
-    const float2 pp = P.prev_pts[f];
+    const float2 pp = sanitize_point(P.prev_pts[f]);
     float2 np = make_float2(0.f, 0.f);
-    if (P.flags & DR3LK_USE_INITIAL_FLOW) np = P.next_pts[f];
+    if (P.flags & DR3LK_USE_INITIAL_FLOW) np = sanitize_point(P.next_pts[f]);
     const float hwx = (P.win_w - 1) * 0.5f, hwy = (P.win_h - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
     const bool want_err = P.err != nullptr;

@@ -295,3 +295,34 @@ print("tma ok")
 ''' % (ROOT, os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DR3LK_TMA="1"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "tma ok" in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("win,ml", [((21, 21), 3), ((31, 31), 4), ((9, 13), 2)])
+def test_lk_non_finite_and_huge_points_are_lost_not_fatal(ctx, dr3, win, ml):
+    """NaN / inf / huge coordinates in prevPts (and in the initial flow): x86 OpenCV's cvFloor saturates them to INT_MIN, every
+    bounds test fails and the point is reported lost with err 0 -- same here, in the specialised and in the generic kernel,
+    and the finite points of the same call are unaffected."""
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    rng = np.random.default_rng(77)
+    good = random_points(rng, a.shape[1], a.shape[0], 400, margin=0)
+    nan, inf, big = np.float32(np.nan), np.float32(np.inf), np.float32(1e30)
+    weird = np.array([[nan, 10], [10, nan], [nan, nan], [inf, 5], [5, -inf], [big, 3], [3, -big], [2.2e9, 1], [1, -2.2e9], [4294967296.0, 7],
+                      [1e-42, 1e-42], [-0.0, -0.0], [a.shape[1] - 1, a.shape[0] - 1]], np.float32)
+    pts = np.concatenate([good[:200], weird, good[200:]]).astype(np.float32)
+    lost = slice(200, 200 + 10)  # the first ten weird points can never be inside a frame
+    with np.errstate(all="ignore"):
+        exp = oracle.calc_optical_flow_pyr_lk(a, b, pts, None, win, ml)
+        got = ctx.calc_optical_flow_pyr_lk(a, b, pts, None, win, ml)
+        assert np.array_equal(got[1], exp[1]) and not got[1][lost].any() and not got[2][lost].any()
+        ok = got[1] == 1
+        assert ok.sum() > 300 and np.array_equal(got[0][ok].view(np.uint32), exp[0][ok].view(np.uint32)) and np.array_equal(got[2], exp[2])
+        # the same garbage as the INITIAL FLOW of otherwise fine points
+        init = pts.copy()
+        init[200:213] = weird[::-1]
+        prev2 = pts.copy()
+        prev2[200:213] = good[:13]
+        exp = oracle.calc_optical_flow_pyr_lk(a, b, prev2, init, win, ml, flags=4)
+        got = ctx.calc_optical_flow_pyr_lk(a, b, prev2, init, win, ml, flags=dr3.USE_INITIAL_FLOW)
+        assert np.array_equal(got[1], exp[1])
+        ok = got[1] == 1
+        assert np.array_equal(got[0][ok].view(np.uint32), exp[0][ok].view(np.uint32)) and np.array_equal(got[2][ok], exp[2][ok])

@@ -59,8 +59,20 @@ def paths(ctx):
     yield "fast detector", lambda: ctx.fast_detect(frames[6])
     p1, s1, _ = ctx.calc_optical_flow_pyr_lk(frames[0], frames[1], pts)
     yield "filter tracks", lambda: ctx.filter_tracks(pts, p1, s1, 718.856, 718.856, 607.19, 185.22)
+    yield "filter tracks (distorted pinhole)", lambda: ctx.filter_tracks(pts, p1, s1, 458.654, 457.296, 367.215, 248.375, (-0.2834, 0.0740, 1.9e-4, 1.8e-5, 0.0))
     F = np.random.default_rng(5).normal(0, 1e-3, (200, 3, 3)).astype(np.float32)
     yield "score fundamental", lambda: ctx.score_fundamental(F, pts[s1 == 1], p1[s1 == 1], 1.0)
+
+    def init_chain():
+        xy, lv, sc, pyr = ctx.init_first_frame(frames[0])
+        k = xy.astype(np.float32)
+        out = ctx.init_second_frame(pyr, frames[1], k, k, fx=718.856, fy=718.856, cx=607.19, cy=185.22)
+        res = ctx.init_score_fundamental(F, len(out["ref"]))
+        pyr.close()
+        return [xy, sc, out["ref"], out["cur"], out["disparity"], out["bearing"], out["status"], res[0], res[1]]
+    yield "init chain (first frame, second frame, scoring)", init_chain
+    mc = dr3.MultiContext([0, 0, 0])
+    yield "multi-context host batch (3 ranks on one device)", lambda: mc.track_batch_host(prev, nxt, allp, offs, want_stats=True)
 
 
 bad = 0
