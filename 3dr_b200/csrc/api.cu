@@ -1006,6 +1006,7 @@ static int pyramid_alloc(dr3lk_ctx* ctx, int w, int h, int win_w, int win_h, int
     for (int l = 0; l <= P.ml; l++) { ioff[l] = img_total; img_total += P.img_bytes[l]; doff[l] = der_total; der_total += P.der_ints[l]; }
     p->der_total = der_total;
     p->img = ctx->take(img_total);
+    p->img.zero_sig = 0;  // whatever the pooled buffer held before, it is an image buffer now (its aprons will not be zeros)
     cudaError_t e = p->img.reserve(img_total);
     if (e == cudaSuccess && with_deriv) {
         p->deriv = ctx->take(der_total * sizeof(int));
