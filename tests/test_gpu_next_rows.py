@@ -214,3 +214,36 @@ def test_set_stream_switch_keeps_results(ctx, dr3):
     finally:
         ctx.set_stream(None)
     assert all(np.array_equal(x, y) for x, y in zip(ctx.calc_optical_flow_pyr_lk(a, b, pts), exp))
+
+
+def test_pooled_pyramid_buffers_changing_roles_stay_correct(ctx, dr3):
+    """Destroyed pyramids hand their device buffers to a pool; a derivative buffer whose zero aprons were cleared once is not
+    cleared again when it is reused for the same layout -- but it must be when it served as an IMAGE buffer in between (the
+    image of a 2x larger frame is about as large as the derivatives of the small one).  Windows hanging over every border read
+    the aprons, so stale apron contents show up as differences against the oracle."""
+    import cv2
+    small_a, small_b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    big_a = cv2.resize(small_a, None, fx=2, fy=2, interpolation=cv2.INTER_LINEAR)
+    big_b = cv2.resize(small_b, None, fx=2, fy=2, interpolation=cv2.INTER_LINEAR)
+    rng = np.random.default_rng(17)
+
+    def border_points(img, n=700):
+        h, w = img.shape
+        p = random_points(rng, w, h, n, margin=25)
+        edge = np.array([[x, y] for x in (-9.5, 0.0, 3.3, w - 4.2, w - 1.0, w + 8.0) for y in (-9.0, 0.0, 2.7, h - 3.1, h - 1.0, h + 7.5)], np.float32)
+        return np.concatenate([p, edge]).astype(np.float32)
+
+    ps, pb = border_points(small_a), border_points(big_a)
+    exp_s = oracle.calc_optical_flow_pyr_lk(small_a, small_b, ps)
+    exp_b = oracle.calc_optical_flow_pyr_lk(big_a, big_b, pb)
+    for rep in range(4):
+        # small frame with derivatives, then destroyed: image + derivative buffers go to the pool
+        p1, p2 = dr3.Pyramid(ctx, small_a), dr3.Pyramid(ctx, small_b)
+        got = ctx.calc_optical_flow_pyr_lk_cached(p1, p2, ps)
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp_s)), ("small", rep)
+        p1.close(); p2.close()
+        # big frames: their Gaussian-only pyramids (keep_next = 1) are about the size of the small frame's derivatives
+        q1 = dr3.Pyramid(ctx, big_a)
+        np_, st, er, q2 = ctx.track_frame(q1, big_b, pb, keep_next=1)
+        assert all(np.array_equal(x, y) for x, y in zip((np_, st, er), exp_b)), ("big", rep)
+        q1.close(); q2.close()
