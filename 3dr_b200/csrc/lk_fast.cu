@@ -170,12 +170,17 @@ struct RunBytes {
     // 2^8 - 512 * I gives (J - I) directly: subtracting a multiple of 512 before the arithmetic shift is exact.
     __device__ __forceinline__ int sample(int k, const Weights& q, int init = 1 << (W_BITS - 5 - 1)) const
     {
+        return sum(k, q, init) >> (W_BITS - 5);
+    }
+    // S + init, before the shift
+    __device__ __forceinline__ int sum(int k, const Weights& q, int init = 1 << (W_BITS - 5 - 1)) const
+    {
         const unsigned tt = (k & 1) ? tO[k >> 2] : tE[k >> 2];
         const unsigned bb = (k & 1) ? bO[k >> 2] : bE[k >> 2];
         int s;
         if (k & 2) { s = dp2a_hi(q.wt, tt, init); s = dp2a_hi(q.wb, bb, s); }
         else { s = dp2a_lo(q.wt, tt, init); s = dp2a_lo(q.wb, bb, s); }
-        return s >> (W_BITS - 5);
+        return s;
     }
 };
 
@@ -473,12 +478,14 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                     }
 #pragma unroll
                     for (int k = 0; k < R; k++) {
-                        const int i5 = rb.sample(k, q);
+                        // 2^8 - 512 * I with I = (S + 2^8) >> 9: clear the low 9 bits of the sum instead of shifting down and
+                        // multiplying up again (two ALU-pipe instructions instead of a shift and an IMAD on the FMA pipe)
+                        const int i_sum = rb.sum(k, q);
                         int ix = (tx[k] * q.w00 + tx[k + 1] * q.w01 + bx[k] * q.w10 + bx[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
                         int iy = (ty[k] * q.w00 + ty[k + 1] * q.w01 + by[k] * q.w10 + by[k + 1] * q.w11 + (1 << (W_BITS - 1))) >> W_BITS;
                         if (G::RAGGED && k >= WW - (G::NCB - 1) * R && rlast[s]) { ix = 0; iy = 0; }  // pixels past the window edge
                         dxr[s][k] = ix; dyr[s][k] = iy;
-                        jinit[s][k] = (1 << (W_BITS - 5 - 1)) - (i5 << (W_BITS - 5));
+                        jinit[s][k] = (1 << (W_BITS - 5 - 1)) - (i_sum & ~((1 << (W_BITS - 5)) - 1));
                         a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
                     }
                 }

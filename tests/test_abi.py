@@ -62,3 +62,43 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(import|from)\s+(oracle|cv2)\b", src, flags=re.M), fn
                 assert not re.search(r"#\s*include\s*[<\"][^>\"]*oracle", src), fn
                 assert "liboracle" not in src and "dlopen" not in src, fn
+
+
+def test_shard_range_rule_without_a_gpu(dr3):
+    """dr3lk_shard_range (the block partition of dr3lk_multi) is host arithmetic: the rule of SURVEY.md 8e and of
+    3dr_b200/sharding.py, for every rank of every world size, incl. more ranks than pairs"""
+    from importlib import import_module
+    sharding = import_module("3dr_b200.sharding")
+    for n in (0, 1, 3, 7, 64, 4096, 32767):
+        for world in (1, 2, 3, 4, 8, 64):
+            blocks = [dr3.shard_range(n, r, world) for r in range(world)]
+            assert blocks == [sharding.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(blocks, blocks[1:]))
+            for p in range(0, n, max(1, n // 50)):  # pair p lives on rank floor(p * world / n) ... within one pair of rounding
+                owner = [r for r, (lo, hi) in enumerate(blocks) if lo <= p < hi]
+                assert len(owner) == 1
+
+
+def test_multi_context_fails_loudly_without_a_device(dr3):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(dr3.Dr3lkError) as e:
+        dr3.MultiContext([0, 0])
+    assert e.value.code == dr3.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_opencv_typed_shim_compiles(tmp_path):
+    """include/dr3lk_opencv.hpp (the two call surfaces with the reference's own cv:: types) and the call-site mirror
+    3dr_b200/host/opencv_callsite.cpp compile warning-free against the stand-in OpenCV types, and the header is inert
+    when no opencv2/core.hpp is on the include path"""
+    inc = os.path.join(ROOT, "include")
+    src = os.path.join(ROOT, "3dr_b200", "host", "opencv_callsite.cpp")
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "mock_opencv"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('#include "dr3lk_opencv.hpp"\n#ifdef DR3LK_HAVE_OPENCV\n#error "no OpenCV here"\n#endif\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", inc, str(probe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
