@@ -200,11 +200,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
-    unsigned done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
+    // the whole wait loop in PTX (try_wait blocks for a hardware-defined time before it returns false)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// exactly one lane of the (converged) warp: lets ptxas issue the TMA from the uniform datapath without a divergence region
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
 }
 // one box of a rank-3 tensor [pair][row][column] at (x, y, pair) -> dense rows at dst (128-byte aligned)
 __device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* map, int x, int y, int pair, uint64_t* bar)
@@ -341,7 +353,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
         if (!o.inb) return;
         const LevelDesc& L = P.lv[level];
         if (TMA) {
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_expect_tx(bars, G::TMA_I_BYTES + G::TMA_D_BYTES);
                 tma_box(sI, &P.tma[level].prev, T::x0_I(o.ipx, L.pitch_p) + G::PX, o.ipy + G::PY, pair, bars);
                 tma_box(sD, &P.tma[level].deriv, T::x0_D(o.ipx, L.dpitch) + G::DPX, o.ipy + G::PY, pair, bars);
@@ -424,7 +436,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 int rx0, ry0;
                 if (TMA) {
                     T::origin_J(L.pitch_n, h, ox, oy, rx0, ry0);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_expect_tx(bars + 1, G::TMA_J_BYTES);
                         tma_box(sJ, &P.tma[level].next, rx0 + G::PX, ry0 + G::PY, pair, bars + 1);
                     }
