@@ -928,12 +928,17 @@ int dr3lk_multi_track_batch_host(dr3lk_multi* m, const uint8_t* prev, const uint
         for (int b = lo; b <= hi; b++) offs[r][b - lo] = pts_offset[b] - p0;
         // every rank owns disjoint slices of the caller's arrays: no exchange, no lock (the "final gather" of SURVEY.md 8e is
         // each device's own D2H copy into its slice)
-        workers.emplace_back([=, &rcs, &offs]() {
+        auto work = [=, &rcs, &offs]() {
             rcs[r] = dr3lk_track_batch_host(m->ctx[r], prev + (size_t)lo * image_stride, next + (size_t)lo * image_stride, w, h, step,
                                             image_stride, hi - lo, prev_pts + 2 * (size_t)p0, next_pts + 2 * (size_t)p0, status + p0,
                                             err ? err + p0 : nullptr, offs[r].data(), stats ? stats + p0 : nullptr, chunk_pairs, win_w,
                                             win_h, max_level, crit_type, crit_max_count, crit_eps, flags, min_eig_threshold);
-        });
+        };
+        try {
+            workers.emplace_back(work);
+        } catch (...) {  // no thread to be had (std::system_error must not cross the C boundary): this rank runs on the calling thread
+            work();
+        }
     }
     for (auto& t : workers) t.join();
     for (int r = 0; r < G; r++)
