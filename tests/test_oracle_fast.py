@@ -1,6 +1,7 @@
 """CPU tests of the FAST-10 / grid-selection restatement (oracle/fast_oracle.c).
-Parity for this row is unpinned (the `fast` library is absent); what can be pinned is checked here: the corner test
-against cv2's FAST-9 by running the same code with arc length 9, and internal consistency of score / non-max / grid."""
+The `fast` library the reference links is absent; what can be pinned is checked here: corner test, score and non-max
+against cv2's FAST-9 by running the same code with arc length 9 (identical key points and responses), the Shi-Tomasi half
+against the reference's own function (tests/test_oracle_vs_ref.py), and internal consistency of score / non-max / grid."""
 import numpy as np
 import pytest
 
@@ -17,6 +18,23 @@ def test_corner_test_matches_cv2_fast9(name):
     cvp = sorted((int(k.pt[1]), int(k.pt[0])) for k in det.detect(im, None))
     mine = sorted((int(y), int(x)) for x, y in oracle.fast_detect(im, 20, 9))
     assert mine == cvp and len(mine) > 1000
+
+
+@pytest.mark.skipif(not cv2_ref.HAVE_CV2, reason="cv2 not importable")
+@pytest.mark.parametrize("name", ["kitti0.png", "kitti_000000.png", "sample_gray_500x375.png"])
+def test_score_and_nonmax_match_cv2_fast9(name):
+    """The whole FAST machinery of the restatement -- arc test, score (largest threshold that keeps the corner) and the 3x3
+    non-maximum suppression -- against OpenCV's FAST with suppression on, at arc length 9: identical key-point sets and
+    identical responses.  The reference's detector (uzh-rpg `fast`, absent here) is the same algorithm at arc length 10:
+    the one constant by which the pinned code path and the used one differ."""
+    im = load_gray(name)
+    det = cv2_ref.cv2.FastFeatureDetector_create(20, True, cv2_ref.cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    cvd = {(int(k.pt[0]), int(k.pt[1])): int(k.response) for k in det.detect(im, None)}
+    xy = oracle.fast_detect(im, 20, 9)
+    sc = oracle.fast_score(im, xy, 20, 9)
+    keep = oracle.fast_nonmax(xy, sc)
+    mine = {(int(xy[i, 0]), int(xy[i, 1])): int(sc[i]) for i in keep}
+    assert len(mine) > 4000 and mine == cvd
 
 
 def test_score_is_largest_threshold_and_nonmax_is_8_neighbour():
