@@ -29,7 +29,7 @@ MAX_LEVELS = 16
 # every symbol include/dr3lk.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
-    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
+    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_debug_check_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
     "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
@@ -67,6 +67,8 @@ def lib():
     L.dr3lk_last_error.restype = ctypes.c_char_p
     L.dr3lk_set_stream.argtypes = [c_void_p, c_void_p]
     L.dr3lk_synchronize.argtypes = [c_void_p]
+    if hasattr(L, "dr3lk_debug_check_read"):
+        L.dr3lk_debug_check_read.argtypes = [c_void_p, P(ctypes.c_uint64)]
     L.dr3lk_launch_count.argtypes = [c_void_p]
     L.dr3lk_launch_count.restype = ctypes.c_uint64
     L.dr3lk_set_profiling.argtypes = [c_void_p, c_int]
@@ -214,6 +216,13 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().dr3lk_launch_count(self._h))
+
+    def debug_check_read(self):
+        """Checked build (DR3LK_LIB=.../libdr3lk_checked.so) only: (violations, first kind, first detail, checks executed)
+        of the LK kernels' own bounds checks since the last read; raises E_UNSUPPORTED with the default library."""
+        out = (ctypes.c_uint64 * 4)()
+        self._check(lib().dr3lk_debug_check_read(self._h, out))
+        return tuple(int(v) for v in out)
 
     # ---- utils::create_img_pyramid ------------------------------------------------------------
     def box_pyramid(self, img, n_levels=3, mode=BOX_AUTO_X86):

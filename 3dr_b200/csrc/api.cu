@@ -514,6 +514,15 @@ int dr3lk_synchronize(dr3lk_ctx* ctx)
 
 uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int dr3lk_debug_check_read(dr3lk_ctx* ctx, unsigned long long* out4)
+{
+    if (!ctx || !out4) return DR3LK_E_ARG;
+    cudaSetDevice(ctx->device);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!lk_fast_check_read(out4)) return fail(ctx, DR3LK_E_UNSUPPORTED, "this library was built without -DDR3LK_CHECKED (make -C 3dr_b200/csrc checked)");
+    return DR3LK_OK;
+}
+
 int dr3lk_set_profiling(dr3lk_ctx* ctx, int on)
 {
     if (!ctx) return DR3LK_E_ARG;

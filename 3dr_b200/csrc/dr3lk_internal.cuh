@@ -124,6 +124,7 @@ struct LkFastBoxes {
     int i_w, i_h, d_w, d_h, j_w, j_h;
 };
 bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b);
+bool lk_fast_check_read(unsigned long long out[4]);  // -DDR3LK_CHECKED builds only
 
 // ---- device helpers ----
 // A NaN coordinate: x86 OpenCV's cvFloor turns it into INT_MIN (cvttss2si's "integer indefinite"), which fails every bounds

@@ -26,6 +26,23 @@
 
 namespace dr3lk {
 
+// ---- checked build (-DDR3LK_CHECKED): compute-sanitizer is not available on the GPU pool, so the specialised kernels can be
+// built with their own bounds checks -- every staged rectangle must lie inside the apron-carrying level allocation it is
+// copied from, every shared-memory load inside the region it reads (and inside the rows that were staged), every output
+// index inside the batch.  Violations are counted in device memory (dr3lk_debug_check_read); the default build has none of it.
+#ifdef DR3LK_CHECKED
+__device__ unsigned long long g_check[4];  // [0] violations, [1] kind of the first, [2] its detail, [3] checks executed (lane 0)
+__device__ __forceinline__ void check_fail(int kind, long long info)
+{
+    if (atomicAdd(&g_check[0], 1ull) == 0) { g_check[1] = (unsigned long long)kind; g_check[2] = (unsigned long long)info; }
+}
+#define DR3LK_CHECK(cond, kind, info) do { if (!(cond)) check_fail(kind, (long long)(info)); } while (0)
+#define DR3LK_CHECK_COUNT() do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_check[3], 1ull); } while (0)
+#else
+#define DR3LK_CHECK(cond, kind, info) do { } while (0)
+#define DR3LK_CHECK_COUNT() do { } while (0)
+#endif
+
 namespace {
 
 
@@ -150,8 +167,11 @@ __device__ __forceinline__ Weights make_weights(float a, float b)
 template <int R, int NWD, int NEO, int PW>
 struct RunBytes {
     unsigned tE[NEO], tO[NEO], bE[NEO], bO[NEO];
-    __device__ __forceinline__ void load(const unsigned* __restrict__ region, int boff)
+    __device__ __forceinline__ void load(const unsigned* __restrict__ region, int boff, int region_words = 0x7fffffff, int staged_bytes = 0x7fffffff)
     {
+        // the two rows start inside the staged rows; the last realignment word may lie behind them but inside the region
+        DR3LK_CHECK(boff >= 0 && boff + PW * 4 + R + 1 <= staged_bytes && (boff >> 2) + PW + NWD <= region_words, 3, boff);
+        DR3LK_CHECK_COUNT();
         const unsigned* p = region + (boff >> 2);
         const unsigned o = boff & 3;
         const unsigned selE = 0x3210u + o * 0x1111u, selO = selE + 0x1111u;
@@ -255,6 +275,15 @@ struct Tracker {
     // x in [-PX, w + PX) and y in [-PY, h + PY) addressable.
     // Search region of the next image around window origin (inx, iny): J_W x J_H bytes from (rx0, ry0); window origins
     // rx0 .. rx0 + J_W - (WW+1), ry0 .. ry0 + 2*MY are inside it.
+    // checked build: the rectangle [first, first + rows x width) read with row step `pitch` lies inside the allocation [lo, hi)
+    // and inside its rows (x0_in_row = byte offset of the rectangle's first column inside an allocation row)
+    static __device__ __forceinline__ void check_rect(const uint8_t* first, int rows, int width, int pitch, int x0_in_row, const uint8_t* lo,
+                                                      const uint8_t* hi, int kind)
+    {
+        DR3LK_CHECK(first >= lo && first + (long long)(rows - 1) * pitch + width <= hi && x0_in_row >= 0 && x0_in_row + width <= pitch, kind,
+                    first - lo);
+        DR3LK_CHECK_COUNT();
+    }
     static __device__ __forceinline__ void origin_J(int pitch, int h, int inx, int iny, int& rx0, int& ry0)
     {
         rx0 = max(-G::PX, min((inx - G::MX) & ~15, pitch - G::PX - G::J_W));
@@ -352,6 +381,25 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     auto issue_template = [&](int pair, const Origin& o, int level) {
         if (!o.inb) return;
         const LevelDesc& L = P.lv[level];
+#ifdef DR3LK_CHECKED
+        {   // the rectangles about to be copied lie inside the apron-carrying allocations of this (pair, level)
+            const uint8_t* im = L.prev + (unsigned long long)(unsigned)pair * L.prev_stride;
+            const uint8_t* lo = im - (G::PY * L.pitch_p + G::PX);
+            const int xi = T::x0_I(o.ipx, L.pitch_p);
+            // (flags bit 30, checked build only: pretend the allocation is one window short at the bottom -- the negative control
+            //  of tests/test_gpu_checked.py, which must then see violations of kind 1 for windows at the lower border)
+            const int short_rows = (P.flags & 0x40000000) ? WH : 0;
+            T::check_rect(im + (o.ipy * L.pitch_p + xi), TMA ? WH + 1 : G::I_ROWS, G::I_W, L.pitch_p, xi + G::PX, lo,
+                          lo + (long long)L.pitch_p * (L.h + 2 * G::PY - short_rows), 1);
+            const int* de = L.deriv + (unsigned long long)(unsigned)pair * L.deriv_stride;
+            const uint8_t* dlo = reinterpret_cast<const uint8_t*>(de - (G::PY * L.dpitch + G::DPX));
+            const int xd = T::x0_D(o.ipx, L.dpitch);
+            T::check_rect(reinterpret_cast<const uint8_t*>(de + (o.ipy * L.dpitch + xd)), TMA ? WH + 1 : G::D_ROWS, G::D_CH * 16, L.dpitch * 4, (xd + G::DPX) * 4, dlo,
+                          dlo + 4ll * L.dpitch * (L.h + 2 * G::PY), 2);
+            // ... and the window itself inside what is staged
+            DR3LK_CHECK(o.ipx - xi >= 0 && o.ipx - xi + WW + 1 <= G::I_W && o.ipx - xd >= 0 && o.ipx - xd + WW + 1 <= G::D_CH * 4, 5, o.ipx);
+        }
+#endif
         if (TMA) {
             if (elect_one()) {
                 mbar_expect_tx(bars, G::TMA_I_BYTES + G::TMA_D_BYTES);
@@ -447,6 +495,15 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 vx0 = max(rx0, -WW); vxs = min(rx0 + (G::J_W - (WW + 1)), w - 1) - vx0;
                 vy0 = max(ry0, -WH); vys = min(ry0 + 2 * G::MY, h - 1) - vy0;
                 jb0 = -(ry0 * (G::J_PW * 4) + rx0);
+#ifdef DR3LK_CHECKED
+                {
+                    const uint8_t* lo = imgJ - (G::PY * L.pitch_n + G::PX);
+                    T::check_rect(imgJ + (ry0 * L.pitch_n + rx0), TMA ? G::J_H : G::J_ROWS, G::J_W, L.pitch_n, rx0 + G::PX, lo,
+                                  lo + (long long)L.pitch_n * (h + 2 * G::PY), 4);
+                    // the origin that triggered the staging is inside the range it produced
+                    DR3LK_CHECK((unsigned)(ox - vx0) <= (unsigned)vxs && (unsigned)(oy - vy0) <= (unsigned)vys, 6, ox);
+                }
+#endif
             };
             auto wait_search = [&]() {
                 if (TMA) {
@@ -479,8 +536,9 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
                     RunBytes<R, G::NWD, G::NEO, G::I_PW> rb;
-                    rb.load(sI, iofs[s] + ox);
+                    rb.load(sI, iofs[s] + ox, G::I_WORDS, G::I_PW * 4 * (WH + 1));
                     const unsigned* dp = sD + dofs[s] + (rvalid[s] ? oxw : 0);
+                    DR3LK_CHECK(dp >= sD && dp + G::D_PW + R + 1 <= sD + G::D_WORDS && (!rvalid[s] || dofs[s] + oxw + G::D_PW + R + 1 <= G::D_PW * (WH + 1) + 4), 7, dofs[s] + oxw);
                     int tx[R + 1], ty[R + 1], bx[R + 1], by[R + 1];
 #pragma unroll
                     for (int k = 0; k <= R; k++) {
@@ -564,14 +622,14 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 const int jbase = iny * (G::J_PW * 4) + inx + jb0;
                 if (G::CACHE_J && jbase != jloaded) {
 #pragma unroll
-                    for (int s = 0; s < NRUN; s++) rbj[s].load(sJ, jbase + jofs[s]);
+                    for (int s = 0; s < NRUN; s++) rbj[s].load(sJ, jbase + jofs[s], G::J_WORDS, G::J_PW * 4 * G::J_H);
                     jloaded = jbase;
                 }
                 int b1 = 0, b2 = 0;
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
                     RunBytes<R, G::NWD, G::NEO, G::J_PW> rbl;
-                    if (!G::CACHE_J) rbl.load(sJ, jbase + jofs[s]);
+                    if (!G::CACHE_J) rbl.load(sJ, jbase + jofs[s], G::J_WORDS, G::J_PW * 4 * G::J_H);
                     const RunBytes<R, G::NWD, G::NEO, G::J_PW>& rb = G::CACHE_J ? rbj[s] : rbl;
 #pragma unroll
                     for (int k = 0; k < R; k++) {
@@ -625,13 +683,13 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
                 const int jbase = iqy * (G::J_PW * 4) + iqx + jb0;
                 if (G::CACHE_J && jbase != jloaded) {
 #pragma unroll
-                    for (int s = 0; s < NRUN; s++) rbj[s].load(sJ, jbase + jofs[s]);
+                    for (int s = 0; s < NRUN; s++) rbj[s].load(sJ, jbase + jofs[s], G::J_WORDS, G::J_PW * 4 * G::J_H);
                 }
                 int es = 0;
 #pragma unroll
                 for (int s = 0; s < NRUN; s++) {
                     RunBytes<R, G::NWD, G::NEO, G::J_PW> rbl;
-                    if (!G::CACHE_J) rbl.load(sJ, jbase + jofs[s]);
+                    if (!G::CACHE_J) rbl.load(sJ, jbase + jofs[s], G::J_WORDS, G::J_PW * 4 * G::J_H);
                     const RunBytes<R, G::NWD, G::NEO, G::J_PW>& rb = G::CACHE_J ? rbj[s] : rbl;
                     int e = 0;
 #pragma unroll
@@ -647,6 +705,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
             }
         }
 
+        DR3LK_CHECK((unsigned)f < (unsigned)P.n_total, 8, f);
         if (lane == 0) {
             P.next_pts[f] = np;
             P.status[f] = (uint8_t)status;
@@ -710,6 +769,19 @@ bool launch_lk_fast(Launch& L, const LKParams& p)
     if (p.win_w == 21) return launch_geo<Geo<21, 21, 7>>(L, p);
     if (p.win_w == 31) return launch_geo<Geo<31, 31, 8>>(L, p);
     return launch_geo<Geo<30, 30, 10>>(L, p);
+}
+
+// checked build: violations / kind / detail / checks executed since the last read (and resets them); false in the default build
+bool lk_fast_check_read(unsigned long long out[4])
+{
+#ifdef DR3LK_CHECKED
+    const unsigned long long zero[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, g_check, sizeof(zero)) != cudaSuccess) return false;
+    return cudaMemcpyToSymbol(g_check, zero, sizeof(zero)) == cudaSuccess;
+#else
+    (void)out;
+    return false;
+#endif
 }
 
 bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b)
