@@ -519,7 +519,13 @@ int dr3lk_debug_check_read(dr3lk_ctx* ctx, unsigned long long* out4)
     if (!ctx || !out4) return DR3LK_E_ARG;
     cudaSetDevice(ctx->device);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!lk_fast_check_read(out4)) return fail(ctx, DR3LK_E_UNSUPPORTED, "this library was built without -DDR3LK_CHECKED (make -C 3dr_b200/csrc checked)");
+    unsigned long long pyr[4] = {0, 0, 0, 0};
+    if (!lk_fast_check_read(out4) || !pyramid_check_read(pyr))
+        return fail(ctx, DR3LK_E_UNSUPPORTED, "this library was built without -DDR3LK_CHECKED (make -C 3dr_b200/csrc checked)");
+    // one set of counters per translation unit: LK kernels (kinds 1..8) + pyramid kernels (kinds 20..)
+    if (out4[0] == 0) { out4[1] = pyr[1]; out4[2] = pyr[2]; }
+    out4[0] += pyr[0];
+    out4[3] += pyr[3];
     return DR3LK_OK;
 }
 

@@ -125,6 +125,34 @@ struct LkFastBoxes {
 };
 bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b);
 bool lk_fast_check_read(unsigned long long out[4]);  // -DDR3LK_CHECKED builds only
+bool pyramid_check_read(unsigned long long out[4]);
+
+// ---- checked build (-DDR3LK_CHECKED): compute-sanitizer is not available on the GPU pool, so the kernels can be built with
+// their own bounds checks -- LK: every staged rectangle must lie inside the apron-carrying level allocation it is copied
+// from, every shared-memory load inside the region it reads (and inside the rows that were staged), every output index
+// inside the batch; pyramid kernels: every store (level pixels, mirrored apron pixels, derivatives) inside the destination
+// image's allocation.  Violations are counted in device memory, one counter set per translation unit, read and summed by
+// dr3lk_debug_check_read; the default build has none of it.
+#ifdef DR3LK_CHECKED
+static __device__ unsigned long long g_check[4];  // [0] violations, [1] kind of the first, [2] its detail, [3] checks executed
+static __device__ __forceinline__ void check_fail(int kind, long long info)
+{
+    if (atomicAdd(&g_check[0], 1ull) == 0) { g_check[1] = (unsigned long long)kind; g_check[2] = (unsigned long long)info; }
+}
+#define DR3LK_CHECK(cond, kind, info) do { if (!(cond)) check_fail(kind, (long long)(info)); } while (0)
+#define DR3LK_CHECK_COUNT() do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_check[3], 1ull); } while (0)
+// reads and resets this translation unit's counters
+static inline bool check_read_tu(unsigned long long out[4])
+{
+    const unsigned long long zero[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, g_check, sizeof(zero)) != cudaSuccess) return false;
+    return cudaMemcpyToSymbol(g_check, zero, sizeof(zero)) == cudaSuccess;
+}
+#else
+#define DR3LK_CHECK(cond, kind, info) do { } while (0)
+#define DR3LK_CHECK_COUNT() do { } while (0)
+static inline bool check_read_tu(unsigned long long*) { return false; }
+#endif
 
 // ---- device helpers ----
 // A NaN coordinate: x86 OpenCV's cvFloor turns it into INT_MIN (cvttss2si's "integer indefinite"), which fails every bounds

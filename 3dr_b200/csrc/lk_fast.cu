@@ -26,23 +26,6 @@
 
 namespace dr3lk {
 
-// ---- checked build (-DDR3LK_CHECKED): compute-sanitizer is not available on the GPU pool, so the specialised kernels can be
-// built with their own bounds checks -- every staged rectangle must lie inside the apron-carrying level allocation it is
-// copied from, every shared-memory load inside the region it reads (and inside the rows that were staged), every output
-// index inside the batch.  Violations are counted in device memory (dr3lk_debug_check_read); the default build has none of it.
-#ifdef DR3LK_CHECKED
-__device__ unsigned long long g_check[4];  // [0] violations, [1] kind of the first, [2] its detail, [3] checks executed (lane 0)
-__device__ __forceinline__ void check_fail(int kind, long long info)
-{
-    if (atomicAdd(&g_check[0], 1ull) == 0) { g_check[1] = (unsigned long long)kind; g_check[2] = (unsigned long long)info; }
-}
-#define DR3LK_CHECK(cond, kind, info) do { if (!(cond)) check_fail(kind, (long long)(info)); } while (0)
-#define DR3LK_CHECK_COUNT() do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_check[3], 1ull); } while (0)
-#else
-#define DR3LK_CHECK(cond, kind, info) do { } while (0)
-#define DR3LK_CHECK_COUNT() do { } while (0)
-#endif
-
 namespace {
 
 
@@ -772,17 +755,7 @@ bool launch_lk_fast(Launch& L, const LKParams& p)
 }
 
 // checked build: violations / kind / detail / checks executed since the last read (and resets them); false in the default build
-bool lk_fast_check_read(unsigned long long out[4])
-{
-#ifdef DR3LK_CHECKED
-    const unsigned long long zero[4] = {0, 0, 0, 0};
-    if (cudaMemcpyFromSymbol(out, g_check, sizeof(zero)) != cudaSuccess) return false;
-    return cudaMemcpyToSymbol(g_check, zero, sizeof(zero)) == cudaSuccess;
-#else
-    (void)out;
-    return false;
-#endif
-}
+bool lk_fast_check_read(unsigned long long out[4]) { return check_read_tu(out); }
 
 bool lk_fast_boxes(int win_w, int win_h, LkFastBoxes* b)
 {

@@ -113,6 +113,8 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
                 o[2] = (int)(__byte_perm(ixe, iye, 0x7632) ^ 0x80008000u);
                 o[3] = (int)(__byte_perm(ixo, iyo, 0x7632) ^ 0x80008000u);
                 int* out = d + (long long)sy * dpitch + sx;
+                DR3LK_CHECK(sx >= 0 && sy >= 0 && sx < dpitch, 20, (long long)sy * dpitch + sx);  // inside the level: the apron is never written
+                DR3LK_CHECK_COUNT();
                 if (sx + 3 < w) {
                     *reinterpret_cast<int4*>(out) = make_int4(o[0], o[1], o[2], o[3]);
                 } else {
@@ -170,6 +172,9 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
                 if (i >= ny) break;
                 uint8_t* row = o + (long long)ys[i] * dst_pitch;
                 uint8_t* out = row + gx;
+                // rows -apron_y .. dh - 1 + apron_y, columns -apron_x .. dst_pitch - apron_x - 1 belong to this image
+                DR3LK_CHECK(ys[i] >= -apron_y && ys[i] <= dh - 1 + apron_y && gx >= 0 && gx < dw && (apron_x > 0 || apron_y == 0), 21, ys[i]);
+                DR3LK_CHECK_COUNT();
                 if (gx + 3 < dw && (dst_pitch & 3) == 0) {
                     *reinterpret_cast<unsigned*>(out) = word;
                 } else {
@@ -183,7 +188,10 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
                         const int x = gx + j, mx = 2 * (dw - 1) - x;
                         if (x >= dw) continue;
                         if (x >= 1 && x <= apron_x) row[-x] = (uint8_t)(v[j] >> 8);
-                        if (x <= dw - 2 && mx <= dw - 1 + apron_x) row[mx] = (uint8_t)(v[j] >> 8);
+                        if (x <= dw - 2 && mx <= dw - 1 + apron_x) {
+                            DR3LK_CHECK(mx >= dw && mx < dst_pitch - apron_x, 22, mx);  // the mirrored column stays inside the row
+                            row[mx] = (uint8_t)(v[j] >> 8);
+                        }
                     }
                 }
             }
@@ -247,7 +255,11 @@ pad_level0_kernel(const uint8_t* __restrict__ src_a, const uint8_t* __restrict__
 #pragma unroll
     for (int k = 0; k < PAD_RPT; k++) {
         const int r = r0 + k * PAD_TY;
-        if (r < h + 2 * ay) *reinterpret_cast<uint4*>(dst + (long long)(r - ay) * dst_pitch) = v[k];
+        if (r < h + 2 * ay) {
+            DR3LK_CHECK(x >= -ax && x + 16 <= dst_pitch - ax && r >= 0, 23, x);  // the chunk lies inside row r of the apron-carrying image
+            DR3LK_CHECK_COUNT();
+            *reinterpret_cast<uint4*>(dst + (long long)(r - ay) * dst_pitch) = v[k];
+        }
     }
 }
 
@@ -348,6 +360,8 @@ void launch_pad_level0(Launch& L, const uint8_t* src_a, const uint8_t* src_b, si
     L.err = cudaGetLastError();
     L.launches++;
 }
+
+bool pyramid_check_read(unsigned long long out[4]) { return check_read_tu(out); }
 
 void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_stride, long long src_img_stride,
                      uint8_t* dst, long long dst_img_stride, int n_img, int sse2_rounding)

@@ -55,7 +55,8 @@ int dr3lk_set_stream(dr3lk_ctx* ctx, void* cuda_stream);
 int dr3lk_synchronize(dr3lk_ctx* ctx);
 /* Checked build only (`make -C 3dr_b200/csrc checked` -> lib/libdr3lk_checked.so, -DDR3LK_CHECKED): the specialised LK kernels
  * verify every staged rectangle against the allocation it is copied from, every shared-memory load against its region and
- * the staged rows, every output index against the batch (compute-sanitizer is not available on the GPU pool).  Returns
+ * the staged rows, every output index against the batch, and the pyramid kernels every store (level pixels, mirrored apron
+ * pixels, derivatives) against the destination image (compute-sanitizer is not available on the GPU pool).  Returns
  * out4 = {violations, kind of the first, its detail, checks executed} since the last read and resets them;
  * DR3LK_E_UNSUPPORTED in the default build, which contains none of the checks. */
 int dr3lk_debug_check_read(dr3lk_ctx* ctx, unsigned long long* out4);
