@@ -29,7 +29,7 @@ MAX_LEVELS = 16
 # every symbol include/dr3lk.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
-    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_debug_check_read", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
+    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_debug_check_read", "dr3lk_debug_set_fast_arc", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
     "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
@@ -69,6 +69,7 @@ def lib():
     L.dr3lk_synchronize.argtypes = [c_void_p]
     if hasattr(L, "dr3lk_debug_check_read"):
         L.dr3lk_debug_check_read.argtypes = [c_void_p, P(ctypes.c_uint64)]
+    L.dr3lk_debug_set_fast_arc.argtypes = [c_void_p, c_int]
     L.dr3lk_launch_count.argtypes = [c_void_p]
     L.dr3lk_launch_count.restype = ctypes.c_uint64
     L.dr3lk_set_profiling.argtypes = [c_void_p, c_int]
@@ -223,6 +224,10 @@ class Context:
         out = (ctypes.c_uint64 * 4)()
         self._check(lib().dr3lk_debug_check_read(self._h, out))
         return tuple(int(v) for v in out)
+
+    def debug_set_fast_arc(self, arc):
+        """Parity hook: 9 makes fast_detect / init_first_frame run OpenCV's FAST-9 segment test instead of the reference's FAST-10."""
+        self._check(lib().dr3lk_debug_set_fast_arc(self._h, int(arc)))
 
     # ---- utils::create_img_pyramid ------------------------------------------------------------
     def box_pyramid(self, img, n_levels=3, mode=BOX_AUTO_X86):

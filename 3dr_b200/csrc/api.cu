@@ -129,6 +129,7 @@ struct dr3lk_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int fast_arc = 10;  // dr3lk_debug_set_fast_arc
     Workspace ws;                 // single-call / device-batch scratch
     HostBuf pinned;               // staging for the single-pair host call
     std::vector<DevBuf> pool;     // device buffers of destroyed dr3lk_pyramid objects, reused by the next create
@@ -513,6 +514,14 @@ int dr3lk_synchronize(dr3lk_ctx* ctx)
 }
 
 uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dr3lk_debug_set_fast_arc(dr3lk_ctx* ctx, int arc)
+{
+    if (!ctx) return DR3LK_E_ARG;
+    if (arc != 9 && arc != 10) return fail(ctx, DR3LK_E_ARG, "fast arc length must be 9 (OpenCV FAST-9, parity hook) or 10 (the reference's detector)");
+    ctx->fast_arc = arc;
+    return DR3LK_OK;
+}
 
 int dr3lk_debug_check_read(dr3lk_ctx* ctx, unsigned long long* out4)
 {
@@ -1398,7 +1407,7 @@ static int fast_detect_impl(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, si
     for (int l = 0; l < n_levels; l++)
         if (lw[l] >= 7 && lh[l] >= 7)
             launch_fast_level(L, dp + off[l], dp + o_score + off[l], lw[l], lh[l], l, fast_threshold, cell_size, gc, (float)detection_threshold,
-                              detection_threshold, occupancy ? dp + o_occ : nullptr, (unsigned long long*)(dp + o_keys));
+                              detection_threshold, occupancy ? dp + o_occ : nullptr, (unsigned long long*)(dp + o_keys), ctx->fast_arc);
     launch_fast_gather(L, (const unsigned long long*)(dp + o_keys), ncell, (const int*)(dp + o_lw), (int*)(dp + o_xy), (int*)(dp + o_lv),
                        (float*)(dp + o_sc), (int*)(dp + o_cnt));
     ctx->launches += L.launches;

@@ -102,7 +102,7 @@ void launch_box_half(Launch& L, const uint8_t* src, int w, int h, long long row_
 
 // fast.cu
 void launch_fast_level(Launch& L, const uint8_t* img, uint8_t* score, int w, int h, int level, int fast_threshold, int cell_size,
-                       int grid_cols, float thr_f, double thr_d, const uint8_t* occupancy, unsigned long long* cell_best);
+                       int grid_cols, float thr_f, double thr_d, const uint8_t* occupancy, unsigned long long* cell_best, int arc = 10);
 void launch_fast_gather(Launch& L, const unsigned long long* cell_best, int n_cells, const int* level_w, int* out_xy, int* out_level,
                         float* out_score, int* n_out);
 

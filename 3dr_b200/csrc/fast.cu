@@ -14,14 +14,18 @@ namespace dr3lk {
 
 namespace {
 
-__device__ __forceinline__ unsigned run10(unsigned m)  // m: 16-bit circular mask; non-zero iff it has 10 contiguous set bits
+// ARC = 10 is the reference's detector (fast_corner_detect_10); ARC = 9 exists so that the same kernels can be pinned against
+// OpenCV's FAST-9 (tests/test_gpu_fast_cv2.py through dr3lk_debug_set_fast_arc) -- the `fast` library itself is absent here.
+template <int ARC>
+__device__ __forceinline__ unsigned run_arc(unsigned m)  // m: 16-bit circular mask; non-zero iff it has ARC contiguous set bits
 {
     const unsigned mm = m | (m << 16);
     const unsigned t2 = mm & (mm >> 1), t4 = t2 & (t2 >> 2), t8 = t4 & (t4 >> 4);
-    return (t8 & (t2 >> 8)) & 0xffffu;
+    return (t8 & ((ARC == 10 ? t2 : mm) >> 8)) & 0xffffu;
 }
 
-// largest over the 16 arcs of 10 contiguous circle positions of the smallest d[] in the arc
+// largest over the 16 arcs of ARC contiguous circle positions of the smallest d[] in the arc
+template <int ARC>
 __device__ __forceinline__ int best_arc_min(const int (&d)[16])
 {
     int m2[16], m4[16], m8[16];
@@ -33,10 +37,11 @@ __device__ __forceinline__ int best_arc_min(const int (&d)[16])
     for (int i = 0; i < 16; i++) m8[i] = min(m4[i], m4[(i + 4) & 15]);
     int best = -1000;
 #pragma unroll
-    for (int i = 0; i < 16; i++) best = max(best, min(m8[i], m2[(i + 8) & 15]));
+    for (int i = 0; i < 16; i++) best = max(best, min(m8[i], ARC == 10 ? m2[(i + 8) & 15] : d[(i + 8) & 15]));
     return best;
 }
 
+template <int ARC>
 __global__ void __launch_bounds__(256)
 fast_score_kernel(const uint8_t* __restrict__ img, int w, int h, int b0, uint8_t* __restrict__ score)
 {
@@ -57,12 +62,12 @@ fast_score_kernel(const uint8_t* __restrict__ img, int w, int h, int b0, uint8_t
             bright |= (d[i] > b0 ? 1u : 0u) << i;
             dark |= (d[i] < -b0 ? 1u : 0u) << i;
         }
-        if (run10(bright) | run10(dark)) {
+        if (run_arc<ARC>(bright) | run_arc<ARC>(dark)) {
             // corner at threshold b  <=>  some arc has all d > b (or all -d > b)  <=>  b <= best - 1
-            const int bb = best_arc_min(d);
+            const int bb = best_arc_min<ARC>(d);
 #pragma unroll
             for (int i = 0; i < 16; i++) d[i] = -d[i];
-            const int bd = best_arc_min(d);
+            const int bd = best_arc_min<ARC>(d);
             out = (uint8_t)min(max(bb, bd) - 1, 254);
         }
     }
@@ -136,11 +141,12 @@ __global__ void fast_gather_kernel(const unsigned long long* __restrict__ cell_b
 }  // namespace
 
 void launch_fast_level(Launch& L, const uint8_t* img, uint8_t* score, int w, int h, int level, int fast_threshold, int cell_size,
-                       int grid_cols, float thr_f, double thr_d, const uint8_t* occupancy, unsigned long long* cell_best)
+                       int grid_cols, float thr_f, double thr_d, const uint8_t* occupancy, unsigned long long* cell_best, int arc)
 {
     if (L.err != cudaSuccess) return;
     dim3 grid((w + 31) / 32, (h + 7) / 8);
-    fast_score_kernel<<<grid, 256, 0, L.stream>>>(img, w, h, fast_threshold, score);
+    if (arc == 9) fast_score_kernel<9><<<grid, 256, 0, L.stream>>>(img, w, h, fast_threshold, score);
+    else fast_score_kernel<10><<<grid, 256, 0, L.stream>>>(img, w, h, fast_threshold, score);
     fast_select_kernel<<<grid, 256, 0, L.stream>>>(img, score, w, h, level, cell_size, grid_cols, thr_f, thr_d, occupancy, cell_best);
     L.err = cudaGetLastError();
     L.launches += 2;

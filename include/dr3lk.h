@@ -60,6 +60,11 @@ int dr3lk_synchronize(dr3lk_ctx* ctx);
  * out4 = {violations, kind of the first, its detail, checks executed} since the last read and resets them;
  * DR3LK_E_UNSUPPORTED in the default build, which contains none of the checks. */
 int dr3lk_debug_check_read(dr3lk_ctx* ctx, unsigned long long* out4);
+/* Parity hook for the corner detector: arc length of the FAST segment test used by dr3lk_fast_detect / dr3lk_init_first_frame
+ * on this context.  10 (the default) is the reference's fast_corner_detect_10 (src/features.cpp:55-66); 9 runs the same
+ * kernels as OpenCV's FAST-9, which is how the tests pin them against cv2 (the `fast` library the reference links is not
+ * available to test against).  Not meant for production use. */
+int dr3lk_debug_set_fast_arc(dr3lk_ctx* ctx, int arc);
 /* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx);
 /* Kernel timing with CUDA events on the launching stream (bench.py's roofline leg).  While profiling is on, every

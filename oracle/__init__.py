@@ -49,7 +49,7 @@ def lib():
         L.orc_fast_nonmax.argtypes = [i16p2, i32p, c_int, i32p]
         L.orc_shi_tomasi.argtypes = [u8p, c_int, c_int, c_long, c_int, c_int]
         L.orc_shi_tomasi.restype = ctypes.c_float
-        L.orc_fast_detector.argtypes = [ctypes.POINTER(u8p), c_int, c_int, c_int, c_int, c_int, c_double, u8p, i32p, i32p, f32p]
+        L.orc_fast_detector_arc.argtypes = [ctypes.POINTER(u8p), c_int, c_int, c_int, c_int, c_int, c_double, u8p, c_int, i32p, i32p, f32p]
         _lib = L
     return _lib
 
@@ -187,7 +187,8 @@ def shi_tomasi(img, u, v):
     return float(lib().orc_shi_tomasi(_p(img, ctypes.c_uint8), img.shape[1], img.shape[0], img.shape[1], int(u), int(v)))
 
 
-def fast_detector(img, n_levels=3, cell_size=30, fast_threshold=20, detection_threshold=20.0, occupancy=None, box_mode=BOX_AUTO_X86):
+def fast_detector(img, n_levels=3, cell_size=30, fast_threshold=20, detection_threshold=20.0, occupancy=None, box_mode=BOX_AUTO_X86,
+                  arc=10):
     """FastDetector::detect on the Frame's box pyramid (src/features.cpp:43-98, src/frame.cpp:13-20).
     Returns (xy (n,2) int32 level-0 coordinates, level (n,), score (n,) float32) in grid-cell order."""
     pyr = [np.ascontiguousarray(p) for p in box_pyramid(img, n_levels, box_mode)]
@@ -198,9 +199,9 @@ def fast_detector(img, n_levels=3, cell_size=30, fast_threshold=20, detection_th
     lv = np.zeros(gc * gr, np.int32)
     sc = np.zeros(gc * gr, np.float32)
     occ = np.ascontiguousarray(occupancy, np.uint8) if occupancy is not None else None
-    n = lib().orc_fast_detector(ptrs, w, h, n_levels, cell_size, fast_threshold, float(detection_threshold),
-                                _p(occ, ctypes.c_uint8) if occ is not None else None, _p(xy, ctypes.c_int32), _p(lv, ctypes.c_int32),
-                                _p(sc, ctypes.c_float))
+    n = lib().orc_fast_detector_arc(ptrs, w, h, n_levels, cell_size, fast_threshold, float(detection_threshold),
+                                    _p(occ, ctypes.c_uint8) if occ is not None else None, int(arc), _p(xy, ctypes.c_int32),
+                                    _p(lv, ctypes.c_int32), _p(sc, ctypes.c_float))
     assert n >= 0
     return xy[:n].copy(), lv[:n].copy(), sc[:n].copy()
 

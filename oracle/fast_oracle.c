@@ -151,10 +151,10 @@ float orc_shi_tomasi(const uint8_t* img, int cols, int rows, long stride, int u,
 /* FastDetector::detect (src/features.cpp:43-98).  levels[l]: continuous (w>>l) x (h>>l) box-pyramid images.
  * occupancy: grid_cols*grid_rows bytes or NULL (all free, as after reset_grid()).  Outputs in grid-cell order:
  * out_xy (level-0 coordinates), out_level, out_score; returns the number of features. */
-int orc_fast_detector(const uint8_t* const* levels, int w, int h, int n_levels, int cell_size, int fast_threshold,
-                      double detection_threshold, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score)
+int orc_fast_detector_arc(const uint8_t* const* levels, int w, int h, int n_levels, int cell_size, int fast_threshold,
+                          double detection_threshold, const uint8_t* occupancy, int arc, int* out_xy, int* out_level, float* out_score)
 {
-    if (!levels || n_levels < 1 || cell_size < 1) return ORC_E_ARG;
+    if (!levels || n_levels < 1 || cell_size < 1 || arc < 9 || arc > 12) return ORC_E_ARG;
     const int gc = (int)ceil((double)w / cell_size), gr = (int)ceil((double)h / cell_size);
     const int ncell = gc * gr;
     int* cx = (int*)calloc((size_t)ncell, sizeof(int));
@@ -167,10 +167,10 @@ int orc_fast_detector(const uint8_t* const* levels, int w, int h, int n_levels, 
         const uint8_t* img = levels[lvl];
         const int cap = lw * lh;
         short* xy = (short*)malloc(sizeof(short) * 2 * (size_t)cap);
-        const int n = orc_fast_detect(img, lw, lh, lw, fast_threshold, 10, xy, cap);
+        const int n = orc_fast_detect(img, lw, lh, lw, fast_threshold, arc, xy, cap);
         int* scores = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
         int* keep = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
-        orc_fast_score(img, lw, xy, n, fast_threshold, 10, scores);
+        orc_fast_score(img, lw, xy, n, fast_threshold, arc, scores);
         const int nk = orc_fast_nonmax(xy, scores, n, keep);
         for (int t = 0; t < nk; t++) {
             const int x = xy[2 * keep[t]], y = xy[2 * keep[t] + 1];
@@ -189,4 +189,13 @@ int orc_fast_detector(const uint8_t* const* levels, int w, int h, int n_levels, 
         }
     free(cx); free(cy); free(cl); free(cs);
     return nf;
+}
+
+/* The reference's detector: arc length 10 (fast_corner_detect_10 / fast_corner_score_10, src/features.cpp:55-72).  The arc
+ * parameter above exists so that the whole detector can be pinned against OpenCV's FAST-9 (tests/test_oracle_fast.py). */
+int orc_fast_detector(const uint8_t* const* levels, int w, int h, int n_levels, int cell_size, int fast_threshold,
+                      double detection_threshold, const uint8_t* occupancy, int* out_xy, int* out_level, float* out_score)
+{
+    return orc_fast_detector_arc(levels, w, h, n_levels, cell_size, fast_threshold, detection_threshold, occupancy, 10, out_xy,
+                                 out_level, out_score);
 }

@@ -86,3 +86,30 @@ def compare_lk(p_a, s_a, e_a, p_b, s_b, e_b, converged=None):
 
 def random_points(rng, w, h, n, margin=40):
     return np.stack([rng.uniform(-margin, w + margin, n), rng.uniform(-margin, h + margin, n)], 1).astype(np.float32)
+
+
+def expected_from_cv2_and_reference(img, n_levels, cell, fast_thr, det_thr, occupancy=None):
+    """FastDetector::detect (src/features.cpp:43-98) with none of the restatement in it: OpenCV FAST-9 + non-max key points on
+    the reference's own reduce_to_half levels, ranked by the reference's own shi_tomasi_score (oracle/_ref), grid rule here."""
+    from oracle import cv2_ref, ref
+    cv2 = cv2_ref.cv2
+    levels = ref.box_pyramid(img, n_levels)
+    h, w = img.shape
+    gc, gr = -(-w // cell), -(-h // cell)
+    best = {}                                                 # cell -> (score, x0, y0, level)
+    det = cv2.FastFeatureDetector_create(fast_thr, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    for lvl, im in enumerate(levels):
+        kps = sorted((int(k.pt[1]), int(k.pt[0])) for k in det.detect(np.ascontiguousarray(im), None))   # raster order
+        if not kps:
+            continue
+        uv = np.array([(x, y) for y, x in kps], np.int32)
+        st = ref.shi_tomasi(im, uv)
+        for (x, y), s in zip(uv, st):
+            k = ((y << lvl) // cell) * gc + (x << lvl) // cell
+            if occupancy is not None and occupancy[k]:
+                continue
+            if s > best.get(k, (np.float32(det_thr),))[0]:     # Corner(0, 0, detection_threshold, 0), strict >
+                best[k] = (s, int(x) << lvl, int(y) << lvl, lvl)
+    cells = [k for k in sorted(best) if best[k][0] > det_thr]
+    xy = np.array([[best[k][1], best[k][2]] for k in cells], np.int32).reshape(-1, 2)
+    return xy, np.array([best[k][3] for k in cells], np.int32), np.array([best[k][0] for k in cells], np.float32)

@@ -69,3 +69,24 @@ def test_detector_grid_properties():
     xy2, _, _ = oracle.fast_detector(im, 3, 30, 20, 20.0, occupancy=occ)
     cells2 = (xy2[:, 1] // 30) * 42 + xy2[:, 0] // 30
     assert set(cells2) == set(cells[1::2])
+
+
+@pytest.mark.skipif(not cv2_ref.HAVE_CV2, reason="cv2 not importable")
+@pytest.mark.parametrize("name", ["kitti0.png", "sample_gray_500x375.png"])
+def test_whole_detector_at_arc9_equals_cv2_plus_reference_functions(name):
+    """FastDetector::detect end to end with nothing of the restatement on the expected side: OpenCV FAST-9 key points on the
+    reference's own reduce_to_half levels, ranked by the reference's own shi_tomasi_score, through the grid rule (numpy)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    from _common import expected_from_cv2_and_reference
+    im = load_gray(name)
+    im = np.ascontiguousarray(im[: im.shape[0] // 4 * 4, : im.shape[1] // 4 * 4])
+    for nl, cell, thr, det in [(3, 30, 20, 20.0), (4, 25, 10, 5.0)]:
+        if nl == 4:
+            im = np.ascontiguousarray(im[: im.shape[0] // 8 * 8, : im.shape[1] // 8 * 8])
+        got = oracle.fast_detector(im, nl, cell, thr, det, arc=9)
+        exp = expected_from_cv2_and_reference(im, nl, cell, thr, det)
+        assert len(exp[0]) > 100
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+        assert np.array_equal(got[2].view(np.uint32), exp[2].view(np.uint32))
