@@ -159,6 +159,22 @@ struct dr3lk_ctx {
     DevBuf tracks;
     int n_tracks = 0;
     size_t tracks_cur_offset = 0;  // byte offset of the compacted current points inside `tracks`
+    // Latency path (a single frame pair): the level-0 apron copy runs on `aux`, beside the chain of level kernels (which then
+    // read the raw level 0 with REFLECT_101 by index), and joins before the LK launch -- see PadFork
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_ready()
+    {
+        if (aux) return true;
+        if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (aux) cudaStreamDestroy(aux);
+            aux = nullptr;
+            return false;
+        }
+        return true;
+    }
     bool profiling = false;
     struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
     std::vector<Prof> prof;
@@ -206,6 +222,37 @@ int check_lk_args(dr3lk_ctx* ctx, int w, int h, const LKArgs& a)
 // Builds both Gaussian pyramids and the Scharr derivatives for `batch` pairs.  prev0/next0: device level-0 images (any
 // alignment).  With aprons (P.ax > 0) level 0 is first copied into its apron-carrying scratch image.  Fills the `lk`
 // level descriptors (pointers at pixel (0, 0)) and lk.fast_ok.  Scratch comes from `W`.
+// The level-0 apron copy of a small batch, off the critical path.  Only the LK kernel reads the apron-carrying level 0: the
+// level kernels can build level 1 and the level-0 derivative from the RAW image (REFLECT_101 by index reflection in the edge
+// tiles), so for a single frame pair -- where the pyramid stage is a chain of dependent ~5 us kernels, not bandwidth -- the pad
+// kernel runs on the context's auxiliary stream beside that chain and is joined before the LK launch.  Large batches keep the
+// one-stream order: there the kernels are HBM-bound and the apron-carrying source is the faster one to read.
+constexpr int kPadForkMaxBatch = 4;
+struct PadFork {
+    dr3lk_ctx* ctx;
+    cudaStream_t main;
+    bool on = false;
+    // raw: the level-0 image(s) the first level kernel would read instead; unaligned rows would put every tile of that kernel
+    // on its byte-wise path, which costs more than the fork saves
+    PadFork(dr3lk_ctx* c, cudaStream_t st, int batch, bool apron, const void* raw, size_t pitch0, size_t stride0) : ctx(c), main(st)
+    {
+        static const bool disabled = getenv("DR3LK_NO_PAD_FORK") != nullptr;  // measurement knob
+        const bool aligned = ((reinterpret_cast<uintptr_t>(raw) | pitch0 | stride0) & 15) == 0;
+        on = apron && aligned && batch <= kPadForkMaxBatch && !disabled && ctx->aux_ready();
+    }
+    // the stream the pad kernel is launched on; everything queued on `main` so far (the uploads) happens before it
+    cudaStream_t begin(Launch& L)
+    {
+        if (!on) return main;
+        if (L.err == cudaSuccess) L.err = cudaEventRecord(ctx->ev_fork, main);
+        if (L.err == cudaSuccess) L.err = cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0);
+        return ctx->aux;
+    }
+    void launched(Launch& L) { if (on && L.err == cudaSuccess) L.err = cudaEventRecord(ctx->ev_join, ctx->aux); }
+    // after the level kernels: whatever follows on `main` (the LK launch, later calls reusing the buffers) waits for the pad
+    void join(Launch& L) { if (on && L.err == cudaSuccess) L.err = cudaStreamWaitEvent(main, ctx->ev_join, 0); }
+};
+
 int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, size_t pitch0,
                    size_t stride0, int batch, const PyrLayout& P, int win_w, int win_h, LKParams& lk)
 {
@@ -258,9 +305,14 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
     lk.fast_ok = apr ? 1 : 0;
 
     Launch L{stream, cudaSuccess, 0};
-    if (apr)
-        launch_pad_level0(L, prev0, next0, pitch0, stride0, const_cast<uint8_t*>(lk.lv[0].prev), const_cast<uint8_t*>(lk.lv[0].next), P.pitch[0],
+    PadFork fork(ctx, stream, batch, apr && (!next0 || ((reinterpret_cast<uintptr_t>(next0) & 15) == 0)), prev0, pitch0, stride0);
+    if (apr) {
+        Launch LP{fork.begin(L), L.err, 0};
+        launch_pad_level0(LP, prev0, next0, pitch0, stride0, const_cast<uint8_t*>(lk.lv[0].prev), const_cast<uint8_t*>(lk.lv[0].next), P.pitch[0],
                           P.img_bytes[0], P.w[0], P.h[0], P.ax, P.ay, batch, next0 ? batch : 0);
+        L.err = LP.err; L.launches += LP.launches;
+        fork.launched(L);
+    }
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = lk.lv[l];
         const bool down = l < P.ml;
@@ -273,6 +325,12 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         a.down = down;
         a.dst_apron_x = P.ax; a.dst_apron_y = P.ay;
         a.src_apron_x = P.ax; a.src_apron_y = P.ay;
+        if (l == 0 && fork.on) {  // the raw images: the apron-carrying copy is being written beside this kernel
+            a.prev_src = prev0; a.next_src = next0;
+            a.prev_src_stride = a.next_src_stride = (unsigned)stride0;
+            a.src_pitch = (int)pitch0;
+            a.src_apron_x = a.src_apron_y = 0;
+        }
         if (down) {
             a.prev_dst = const_cast<uint8_t*>(lk.lv[l + 1].prev); a.next_dst = const_cast<uint8_t*>(lk.lv[l + 1].next);
             a.prev_dst_stride = lk.lv[l + 1].prev_stride; a.next_dst_stride = lk.lv[l + 1].next_stride;
@@ -280,6 +338,7 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         }
         launch_pyr_level(L, a);
     }
+    fork.join(L);
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pyramid kernel launch");
     return DR3LK_OK;
@@ -485,6 +544,7 @@ void dr3lk_destroy(dr3lk_ctx* ctx)
         ctx->slot_ws[i].release();
         if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
     }
+    if (ctx->aux) { cudaStreamDestroy(ctx->aux); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -727,6 +787,28 @@ int dr3lk_track_batch(dr3lk_ctx* ctx, const uint8_t* prev_dev, const uint8_t* ne
                               next_pts_dev, status_dev, err_dev, pts_offset, (const int*)ctx->ws.offs.p, n_total, stats_dev, a);
 }
 
+// True when the image can go to the copy engine as it is: page-locked host memory (dr3lk_host_alloc, cudaHostAlloc,
+// cudaHostRegister) whose rows already sit at the device pitch, so that the upload is ONE contiguous copy and the staging
+// memcpy into the context's pinned mirror (~15 us per KITTI frame) is skipped.  Pinned rows at any other step are packed like
+// pageable ones: a 2-D DMA of 1241-byte rows was measured 36 us per call SLOWER than packing (profiles/README.md, round 2).
+static bool direct_upload(const void* img, size_t step, int pitch0)
+{
+    if (step != (size_t)pitch0) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, img) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+static size_t direct_bytes(size_t step, int w, int h) { return (size_t)(h - 1) * step + (size_t)w; }  // never past the last pixel
+
+// Level-0 upload of one image (rows of w bytes at `step`) to device rows at pitch0.  The caller synchronises the stream
+// before it returns to its own caller, so the source only has to stay valid for the duration of the call.
+static cudaError_t upload_image(uint8_t* dev, uint8_t* stage, int pitch0, const uint8_t* img, size_t step, int w, int h, cudaStream_t st)
+{
+    if (direct_upload(img, step, pitch0)) return cudaMemcpyAsync(dev, img, direct_bytes(step, w, h), cudaMemcpyHostToDevice, st);
+    for (int y = 0; y < h; y++) memcpy(stage + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
+    return cudaMemcpyAsync(dev, stage, (size_t)pitch0 * h, cudaMemcpyHostToDevice, st);
+}
+
 int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t prev_step, const uint8_t* next, size_t next_step,
                                    int w, int h, const float* prev_pts, float* next_pts, uint8_t* status, float* err, int n,
                                    int win_w, int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps,
@@ -756,15 +838,18 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     // The previous image crosses PCIe while the host is still packing the next one: two copies, the first one hidden behind
     // the second memcpy (the staging memcpy of ~0.5 MB per image is as long as its DMA)
-    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
-    CU_TRY(ctx, cudaMemcpyAsync(dp, hp, img_bytes, cudaMemcpyHostToDevice, st));
-    for (int y = 0; y < h; y++) memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
+    // (pinned images whose rows sit at the device pitch skip the packing altogether)
+    CU_TRY(ctx, upload_image(dp, hp, pitch0, prev, prev_step, w, h, st));
+    const bool next_pinned = direct_upload(next, next_step, pitch0);
+    if (next_pinned) CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, next, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st));
+    else for (int y = 0; y < h; y++) memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
     memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
     const int offs[2] = {0, n};
     memcpy(hp + o_offs, offs, sizeof(offs));
     size_t in_bytes = o_next;
     if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
-    CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, hp + img_bytes, in_bytes - img_bytes, cudaMemcpyHostToDevice, st));
+    const size_t in_from = next_pinned ? o_prev : img_bytes;  // the points ride behind the next image when it was packed
+    CU_TRY(ctx, cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st));
     rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(dp + o_prev), (float*)(dp + o_next),
                             dp + o_status, err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
     if (rc != DR3LK_OK) return rc;
@@ -1075,6 +1160,7 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
     const PyrLayout& P = p->P;
     const size_t l0_bytes = pitch0 * p->h;
     if (L.err != cudaSuccess) return;
+    PadFork fork(ctx, st, 1, P.ax > 0, l0_dev, pitch0, 0);
     if (P.ax > 0) {
         // level 0 is copied into its apron-carrying image; the derivative aprons are zeros: cleared once per (buffer, layout)
         if (p->has_deriv) {
@@ -1085,8 +1171,11 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
                 p->deriv.zero_sig = sig;
             }
         }
-        launch_pad_level0(L, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
+        Launch LP{fork.begin(L), L.err, 0};
+        launch_pad_level0(LP, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
                           p->h, P.ax, P.ay, 1, 0);
+        L.err = LP.err; L.launches += LP.launches;
+        fork.launched(L);
     } else {
         L.err = cudaMemcpy2DAsync(p->img.p, P.pitch[0], l0_dev, pitch0, p->w, p->h, cudaMemcpyDeviceToDevice, st);
     }
@@ -1101,9 +1190,14 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
         if (!pa.down && !pa.deriv) break;  // nothing to produce from the last level
         pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
         pa.src_apron_x = P.ax; pa.src_apron_y = P.ay;
+        if (l == 0 && fork.on) {  // the raw image, see PadFork
+            pa.prev_src = l0_dev; pa.prev_src_stride = (unsigned)l0_bytes; pa.src_pitch = (int)pitch0;
+            pa.src_apron_x = pa.src_apron_y = 0;
+        }
         if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
         launch_pyr_level(L, pa);
     }
+    fork.join(L);
     ctx->launches += L.launches;
     L.launches = 0;
 }
@@ -1142,9 +1236,8 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     if (e == cudaSuccess) e = ctx->ws.lvl0_prev.reserve(l0_bytes);
     if (e != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, e, "pyramid_create: allocation"); }
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
     Launch L{st, cudaSuccess, 0};
-    L.err = cudaMemcpyAsync(ctx->ws.lvl0_prev.p, hp, l0_bytes, cudaMemcpyHostToDevice, st);
+    L.err = upload_image((uint8_t*)ctx->ws.lvl0_prev.p, hp, pitch0, img, step, w, h, st);
     pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, pitch0, st, L);
     // the pinned staging buffer is reused by the next call: wait for the upload
     if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st);
@@ -1254,7 +1347,11 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
     if (e != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame: allocation"); }
     uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, next_img + (size_t)y * next_step, (size_t)w);
+    // a pinned image at the device pitch goes to the copy engine as it is; any other is packed in front of the points (one copy for both)
+    const bool img_pinned = direct_upload(next_img, next_step, pitch0);
+    Launch L{st, cudaSuccess, 0};
+    if (img_pinned) L.err = cudaMemcpyAsync(dp, next_img, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st);
+    else for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, next_img + (size_t)y * next_step, (size_t)w);
     const int offs[2] = {0, n};
     size_t in_bytes = img_block;
     if (n > 0) {
@@ -1263,8 +1360,8 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
         in_bytes = o_next;
         if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
     }
-    Launch L{st, cudaSuccess, 0};
-    L.err = cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st);
+    const size_t in_from = img_pinned ? o_prev : 0;
+    if (L.err == cudaSuccess && in_bytes > in_from) L.err = cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st);
     pyramid_enqueue(ctx, p2, dp, pitch0, st, L);
     if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
     if (n > 0) {

@@ -247,3 +247,51 @@ def test_pooled_pyramid_buffers_changing_roles_stay_correct(ctx, dr3):
         np_, st, er, q2 = ctx.track_frame(q1, big_b, pb, keep_next=1)
         assert all(np.array_equal(x, y) for x, y in zip((np_, st, er), exp_b)), ("big", rep)
         q1.close(); q2.close()
+
+
+def test_page_locked_images_skip_the_staging_copy_and_change_nothing(ctx, dr3):
+    """Images in page-locked memory (dr3lk_host_alloc) whose rows sit at the device pitch (width rounded up to 16) are handed
+    to the copy engine directly instead of being packed into the context's mirror; pinned images at any other step are packed
+    like pageable ones.  Whole frames and a strided ROI inside a pinned frame, through the two-image call,
+    dr3lk_pyramid_create and dr3lk_track_frame -- results identical to pageable inputs and to the oracle."""
+    frames = [load_gray("kitti%d.png" % i) for i in range(3)]
+    h, w = frames[0].shape
+    pts = golden_case("c1_default_21x21")["prev_pts"][:1200]
+    pins = [dr3.PinnedArray((h, (w + 15) // 16 * 16), np.uint8) for _ in frames]
+    for pa, f in zip(pins, frames):
+        pa.array[...] = 0xA5                                   # the pad columns hold garbage that must never be read as pixels
+        pa.array[:, :w] = f
+    pf = [pa.array[:, :w] for pa in pins]                      # row step == device pitch: the direct path
+    assert pf[0].strides[0] == (w + 15) // 16 * 16 and w % 16 != 0
+    orc = oracle.calc_optical_flow_pyr_lk(frames[0], frames[1], pts)
+    for a_img, b_img in [(pf[0], pf[1]), (pf[0], frames[1]), (frames[0], pf[1])]:   # either side pinned
+        got = ctx.calc_optical_flow_pyr_lk(a_img, b_img, pts)
+        assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc))
+    # a strided ROI of pinned frames: odd width, row step not the device pitch of that width -> packed
+    r0, r1 = pf[0][11:311, 37:900], pf[1][11:311, 37:900]
+    assert not r0.flags["C_CONTIGUOUS"]
+    q = (pts[(pts[:, 0] < 850) & (pts[:, 1] < 290)] + np.float32(3.25))[:600]
+    got = ctx.calc_optical_flow_pyr_lk(r0, r1, q, None, (21, 21), 3, (3, 30, 0.01), 0)
+    exp = oracle.calc_optical_flow_pyr_lk(np.ascontiguousarray(r0), np.ascontiguousarray(r1), q)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp))
+    # a band of full-width rows: same step, fewer rows -> direct, and the copy must stop at the last pixel of the last row
+    r0, r1 = pf[0][5:205], pf[1][5:205]
+    q = pts[pts[:, 1] < 195][:600]
+    got = ctx.calc_optical_flow_pyr_lk(r0, r1, q)
+    exp = oracle.calc_optical_flow_pyr_lk(np.ascontiguousarray(r0), np.ascontiguousarray(r1), q)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp))
+    # cached pyramids and the streaming call
+    prev = dr3.Pyramid(ctx, pf[0], (21, 21), 3)
+    p, s, e, nxt = ctx.track_frame(prev, pf[1], pts, keep_next=2)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip((p, s, e), orc))
+    p2, s2, e2, _ = ctx.track_frame(nxt, pf[2], p[s == 1], keep_next=0)
+    orc2 = oracle.calc_optical_flow_pyr_lk(frames[1], frames[2], p[s == 1])
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip((p2, s2, e2), orc2))
+    # no points, pinned image: only the pyramid is built
+    _, _, _, only = ctx.track_frame(prev, pf[2], np.zeros((0, 2), np.float32), keep_next=2)
+    got = ctx.calc_optical_flow_pyr_lk_cached(nxt, only, p[s == 1])
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc2))
+    for x in (prev, nxt, only):
+        x.close()
+    for pa in pins:
+        pa.free()
