@@ -159,22 +159,6 @@ struct dr3lk_ctx {
     DevBuf tracks;
     int n_tracks = 0;
     size_t tracks_cur_offset = 0;  // byte offset of the compacted current points inside `tracks`
-    // Latency path (a single frame pair): the level-0 apron copy runs on `aux`, beside the chain of level kernels (which then
-    // read the raw level 0 with REFLECT_101 by index), and joins before the LK launch -- see PadFork
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool aux_ready()
-    {
-        if (aux) return true;
-        if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            if (aux) cudaStreamDestroy(aux);
-            aux = nullptr;
-            return false;
-        }
-        return true;
-    }
     bool profiling = false;
     struct Prof { cudaEvent_t e[3]; };  // pyramid start, LK start, LK end
     std::vector<Prof> prof;
@@ -222,36 +206,17 @@ int check_lk_args(dr3lk_ctx* ctx, int w, int h, const LKArgs& a)
 // Builds both Gaussian pyramids and the Scharr derivatives for `batch` pairs.  prev0/next0: device level-0 images (any
 // alignment).  With aprons (P.ax > 0) level 0 is first copied into its apron-carrying scratch image.  Fills the `lk`
 // level descriptors (pointers at pixel (0, 0)) and lk.fast_ok.  Scratch comes from `W`.
-// The level-0 apron copy of a small batch, off the critical path.  Only the LK kernel reads the apron-carrying level 0: the
-// level kernels can build level 1 and the level-0 derivative from the RAW image (REFLECT_101 by index reflection in the edge
-// tiles), so for a single frame pair -- where the pyramid stage is a chain of dependent ~5 us kernels, not bandwidth -- the pad
-// kernel runs on the context's auxiliary stream beside that chain and is joined before the LK launch.  Large batches keep the
-// one-stream order: there the kernels are HBM-bound and the apron-carrying source is the faster one to read.
-constexpr int kPadForkMaxBatch = 4;
-struct PadFork {
-    dr3lk_ctx* ctx;
-    cudaStream_t main;
-    bool on = false;
-    // raw: the level-0 image(s) the first level kernel would read instead; unaligned rows would put every tile of that kernel
-    // on its byte-wise path, which costs more than the fork saves
-    PadFork(dr3lk_ctx* c, cudaStream_t st, int batch, bool apron, const void* raw, size_t pitch0, size_t stride0) : ctx(c), main(st)
-    {
-        static const bool disabled = getenv("DR3LK_NO_PAD_FORK") != nullptr;  // measurement knob
-        const bool aligned = ((reinterpret_cast<uintptr_t>(raw) | pitch0 | stride0) & 15) == 0;
-        on = apron && aligned && batch <= kPadForkMaxBatch && !disabled && ctx->aux_ready();
-    }
-    // the stream the pad kernel is launched on; everything queued on `main` so far (the uploads) happens before it
-    cudaStream_t begin(Launch& L)
-    {
-        if (!on) return main;
-        if (L.err == cudaSuccess) L.err = cudaEventRecord(ctx->ev_fork, main);
-        if (L.err == cudaSuccess) L.err = cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0);
-        return ctx->aux;
-    }
-    void launched(Launch& L) { if (on && L.err == cudaSuccess) L.err = cudaEventRecord(ctx->ev_join, ctx->aux); }
-    // after the level kernels: whatever follows on `main` (the LK launch, later calls reusing the buffers) waits for the pad
-    void join(Launch& L) { if (on && L.err == cudaSuccess) L.err = cudaStreamWaitEvent(main, ctx->ev_join, 0); }
-};
+// Latency path (a few frame pairs at most): the pyramid stage is a chain of small dependent kernels, launched with
+// programmatic stream serialization (Launch::pdl).  Measured on one box (tools/latency_ab.sh, profiles/latency_r02_ab.txt): PDL
+// takes 9 us off a 106 us call.  Running the level-0 apron copy on a second stream beside the level kernels was also tried: it
+// shortens the stage without PDL (35.6 -> 30.8 us) but costs 2 us with it (the event join breaks a dependent-launch edge and
+// the first level kernel reads the raw image through its slower edge path), so it is not done.
+constexpr int kLatencyMaxBatch = 4;
+static bool pdl_enabled()
+{
+    static const bool on = getenv("DR3LK_NO_PDL") == nullptr;  // measurement knob
+    return on;
+}
 
 int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev0, const uint8_t* next0, size_t pitch0,
                    size_t stride0, int batch, const PyrLayout& P, int win_w, int win_h, LKParams& lk)
@@ -305,14 +270,10 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
     lk.fast_ok = apr ? 1 : 0;
 
     Launch L{stream, cudaSuccess, 0};
-    PadFork fork(ctx, stream, batch, apr && (!next0 || ((reinterpret_cast<uintptr_t>(next0) & 15) == 0)), prev0, pitch0, stride0);
-    if (apr) {
-        Launch LP{fork.begin(L), L.err, 0};
-        launch_pad_level0(LP, prev0, next0, pitch0, stride0, const_cast<uint8_t*>(lk.lv[0].prev), const_cast<uint8_t*>(lk.lv[0].next), P.pitch[0],
+    L.pdl = batch <= kLatencyMaxBatch && pdl_enabled();  // latency path: dependent launches overlap the tail of their predecessor
+    if (apr)
+        launch_pad_level0(L, prev0, next0, pitch0, stride0, const_cast<uint8_t*>(lk.lv[0].prev), const_cast<uint8_t*>(lk.lv[0].next), P.pitch[0],
                           P.img_bytes[0], P.w[0], P.h[0], P.ax, P.ay, batch, next0 ? batch : 0);
-        L.err = LP.err; L.launches += LP.launches;
-        fork.launched(L);
-    }
     for (int l = 0; l <= P.ml; l++) {
         const LevelDesc& s = lk.lv[l];
         const bool down = l < P.ml;
@@ -325,12 +286,6 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         a.down = down;
         a.dst_apron_x = P.ax; a.dst_apron_y = P.ay;
         a.src_apron_x = P.ax; a.src_apron_y = P.ay;
-        if (l == 0 && fork.on) {  // the raw images: the apron-carrying copy is being written beside this kernel
-            a.prev_src = prev0; a.next_src = next0;
-            a.prev_src_stride = a.next_src_stride = (unsigned)stride0;
-            a.src_pitch = (int)pitch0;
-            a.src_apron_x = a.src_apron_y = 0;
-        }
         if (down) {
             a.prev_dst = const_cast<uint8_t*>(lk.lv[l + 1].prev); a.next_dst = const_cast<uint8_t*>(lk.lv[l + 1].next);
             a.prev_dst_stride = lk.lv[l + 1].prev_stride; a.next_dst_stride = lk.lv[l + 1].next_stride;
@@ -338,7 +293,6 @@ int build_pyramids(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint
         }
         launch_pyr_level(L, a);
     }
-    fork.join(L);
     ctx->launches += L.launches;
     if (L.err != cudaSuccess) return fail_cuda(ctx, L.err, "pyramid kernel launch");
     return DR3LK_OK;
@@ -421,6 +375,7 @@ void fill_tma(dr3lk_ctx* ctx, LKParams& lk, int batch)
 int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk, Workspace& W)
 {
     Launch L{stream, cudaSuccess, 0};
+    L.pdl = lk.batch <= kLatencyMaxBatch && pdl_enabled();  // latency path, see Launch::pdl
     if (launch_lk_fast(L, lk)) W.epoch++;  // the persistent kernel consumed one work counter and re-armed the other
     else launch_lk_generic(L, lk);
     ctx->launches += L.launches;
@@ -431,11 +386,12 @@ int run_lk(dr3lk_ctx* ctx, cudaStream_t stream, const LKParams& lk, Workspace& W
 // LK over level descriptors that are already filled in (lk.lv[0..max_level], lk.max_level, lk.fast_ok).
 int run_tracking(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, LKParams& lk, int batch, const float* prev_pts_dev,
                  float* next_pts_dev, uint8_t* status_dev, float* err_dev, const int* pts_offset, const int* pts_offset_dev, int n_total,
-                 uint32_t* stats_dev, const LKArgs& a)
+                 uint32_t* stats_dev, const LKArgs& a, float* next_out_dev = nullptr)
 {
     fill_lk_scalars(lk, a);
     lk.prev_pts = (const float2*)prev_pts_dev;
     lk.next_pts = (float2*)next_pts_dev;
+    lk.next_out = (float2*)(next_out_dev ? next_out_dev : next_pts_dev);
     lk.status = status_dev;
     lk.err = err_dev;
     lk.stats = stats_dev;
@@ -468,7 +424,7 @@ int run_tracking(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, LKParams& lk
 int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const uint8_t* prev_dev, const uint8_t* next_dev, int w,
                        int h, size_t pitch, size_t image_stride, int batch, const float* prev_pts_dev, float* next_pts_dev,
                        uint8_t* status_dev, float* err_dev, const int* pts_offset, const int* pts_offset_dev, int n_total,
-                       uint32_t* stats_dev, const LKArgs& a)
+                       uint32_t* stats_dev, const LKArgs& a, float* next_out_dev = nullptr)
 {
     // the pyramid kernels put the image index (both frames of every pair) in gridDim.z
     if (batch > 32767) return fail(ctx, DR3LK_E_SIZE, "at most 32767 frame pairs per device-resident call: split the batch");
@@ -484,7 +440,7 @@ int track_batch_device(dr3lk_ctx* ctx, Workspace& W, cudaStream_t stream, const 
     if (rc != DR3LK_OK) return rc;
     if (ctx->profiling) CU_TRY(ctx, cudaEventRecord(pr.e[1], stream));
     rc = run_tracking(ctx, W, stream, lk, batch, prev_pts_dev, next_pts_dev, status_dev, err_dev, pts_offset, pts_offset_dev, n_total,
-                      stats_dev, a);
+                      stats_dev, a, next_out_dev);
     if (ctx->profiling) {
         CU_TRY(ctx, cudaEventRecord(pr.e[2], stream));
         ctx->prof.push_back(pr);
@@ -544,7 +500,6 @@ void dr3lk_destroy(dr3lk_ctx* ctx)
         ctx->slot_ws[i].release();
         if (ctx->slot_stream[i]) cudaStreamDestroy(ctx->slot_stream[i]);
     }
-    if (ctx->aux) { cudaStreamDestroy(ctx->aux); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -787,6 +742,25 @@ int dr3lk_track_batch(dr3lk_ctx* ctx, const uint8_t* prev_dev, const uint8_t* ne
                               next_pts_dev, status_dev, err_dev, pts_offset, (const int*)ctx->ws.offs.p, n_total, stats_dev, a);
 }
 
+// Latency path: the LK kernel writes next_pts / status / err of a single call straight into the context's pinned mirror
+// (mapped into the device's address space under unified addressing), so that no device-to-host copy is queued behind it:
+// the results are in host memory when the stream synchronises.  Returns the device alias of `host` or nullptr (more points
+// than the posted PCIe writes are worth, or no mapping: the caller then copies back as before).
+constexpr int kDirectOutMaxPoints = 16384;
+static bool mapped_points_enabled()
+{
+    static const bool on = getenv("DR3LK_NO_MAPPED_PTS") == nullptr;  // measurement knob
+    return on;
+}
+static uint8_t* mapped_alias(void* host, int n)
+{
+    static const bool disabled = getenv("DR3LK_NO_DIRECT_OUT") != nullptr;  // measurement knob
+    if (disabled || n > kDirectOutMaxPoints) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, host, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (uint8_t*)d;
+}
+
 // True when the image can go to the copy engine as it is: page-locked host memory (dr3lk_host_alloc, cudaHostAlloc,
 // cudaHostRegister) whose rows already sit at the device pitch, so that the upload is ONE contiguous copy and the staging
 // memcpy into the context's pinned mirror (~15 us per KITTI frame) is skipped.  Pinned rows at any other step are packed like
@@ -848,12 +822,20 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     memcpy(hp + o_offs, offs, sizeof(offs));
     size_t in_bytes = o_next;
     if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
-    const size_t in_from = next_pinned ? o_prev : img_bytes;  // the points ride behind the next image when it was packed
-    CU_TRY(ctx, cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st));
-    rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(dp + o_prev), (float*)(dp + o_next),
-                            dp + o_status, err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
+    uint8_t* const out = mapped_alias(hp, n);  // results straight into the pinned mirror, or ...
+    uint8_t* const ob = out ? out : dp;
+    // The points ride behind the next image when it was packed.  When it was not (pinned frames), a third copy would sit in
+    // front of the kernels for a few hundred bytes: the LK kernel reads the points from the mapped mirror instead.
+    const bool mapped_pts = next_pinned && out && mapped_points_enabled();
+    const size_t in_from = next_pinned ? o_prev : img_bytes;
+    if (!mapped_pts) CU_TRY(ctx, cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st));
+    const uint8_t* const pb = mapped_pts ? out : dp;
+    // (the device copy of the offsets is only read for batches with differing point counts)
+    rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(pb + o_prev), (float*)(pb + o_next),
+                            ob + o_status, err ? (float*)(ob + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a,
+                            (float*)(ob + o_next));
     if (rc != DR3LK_OK) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));
+    if (!out) CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));  // ... one copy back
     CU_TRY(ctx, cudaStreamSynchronize(st));
     memcpy(next_pts, hp + o_next, 8 * (size_t)n);
     memcpy(status, hp + o_status, (size_t)n);
@@ -1160,7 +1142,8 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
     const PyrLayout& P = p->P;
     const size_t l0_bytes = pitch0 * p->h;
     if (L.err != cudaSuccess) return;
-    PadFork fork(ctx, st, 1, P.ax > 0, l0_dev, pitch0, 0);
+    const bool pdl_before = L.pdl;
+    L.pdl = pdl_enabled();  // one frame: a chain of small dependent kernels, see Launch::pdl
     if (P.ax > 0) {
         // level 0 is copied into its apron-carrying image; the derivative aprons are zeros: cleared once per (buffer, layout)
         if (p->has_deriv) {
@@ -1171,11 +1154,8 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
                 p->deriv.zero_sig = sig;
             }
         }
-        Launch LP{fork.begin(L), L.err, 0};
-        launch_pad_level0(LP, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
+        launch_pad_level0(L, l0_dev, nullptr, pitch0, l0_bytes, const_cast<uint8_t*>(p->lv[0].prev), nullptr, P.pitch[0], P.img_bytes[0], p->w,
                           p->h, P.ax, P.ay, 1, 0);
-        L.err = LP.err; L.launches += LP.launches;
-        fork.launched(L);
     } else {
         L.err = cudaMemcpy2DAsync(p->img.p, P.pitch[0], l0_dev, pitch0, p->w, p->h, cudaMemcpyDeviceToDevice, st);
     }
@@ -1190,14 +1170,10 @@ static void pyramid_enqueue(dr3lk_ctx* ctx, dr3lk_pyramid* p, const uint8_t* l0_
         if (!pa.down && !pa.deriv) break;  // nothing to produce from the last level
         pa.dst_apron_x = P.ax; pa.dst_apron_y = P.ay;
         pa.src_apron_x = P.ax; pa.src_apron_y = P.ay;
-        if (l == 0 && fork.on) {  // the raw image, see PadFork
-            pa.prev_src = l0_dev; pa.prev_src_stride = (unsigned)l0_bytes; pa.src_pitch = (int)pitch0;
-            pa.src_apron_x = pa.src_apron_y = 0;
-        }
         if (pa.down) { pa.prev_dst = const_cast<uint8_t*>(p->lv[l + 1].prev); pa.prev_dst_stride = p->lv[l + 1].prev_stride; pa.dst_pitch = p->lv[l + 1].pitch_p; }
         launch_pyr_level(L, pa);
     }
-    fork.join(L);
+    L.pdl = pdl_before;
     ctx->launches += L.launches;
     L.launches = 0;
 }
@@ -1300,10 +1276,12 @@ int dr3lk_calc_optical_flow_pyr_lk_cached(dr3lk_ctx* ctx, const dr3lk_pyramid* p
     size_t in_bytes = o_next;
     if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
     CU_TRY(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
-    rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status,
-                      err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
+    uint8_t* const out = mapped_alias(hp, n);
+    uint8_t* const ob = out ? out : dp;
+    rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), ob + o_status,
+                      err ? (float*)(ob + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a, (float*)(ob + o_next));
     if (rc != DR3LK_OK) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));
+    if (!out) CU_TRY(ctx, cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     memcpy(next_pts, hp + o_next, 8 * (size_t)n);
     memcpy(status, hp + o_status, (size_t)n);
@@ -1361,7 +1339,10 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
         if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
     }
     const size_t in_from = img_pinned ? o_prev : 0;
-    if (L.err == cudaSuccess && in_bytes > in_from) L.err = cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st);
+    uint8_t* const out = n > 0 ? mapped_alias(hp, n) : nullptr;  // results (and, with a pinned image, the points) through the mapped mirror
+    const bool mapped_pts = img_pinned && out && mapped_points_enabled();                    // no second copy in front of the kernels for a few hundred bytes
+    if (L.err == cudaSuccess && in_bytes > in_from && !mapped_pts)
+        L.err = cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st);
     pyramid_enqueue(ctx, p2, dp, pitch0, st, L);
     if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
     if (n > 0) {
@@ -1376,10 +1357,12 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
         }
         lk.max_level = ml;
         lk.fast_ok = prev->P.ax > 0;
-        rc = run_tracking(ctx, W, st, lk, 1, (const float*)(dp + o_prev), (float*)(dp + o_next), dp + o_status,
-                          err ? (float*)(dp + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a);
+        uint8_t* const ob = out ? out : dp;
+        const uint8_t* const pb = mapped_pts ? out : dp;
+        rc = run_tracking(ctx, W, st, lk, 1, (const float*)(pb + o_prev), (float*)(pb + o_next), ob + o_status,
+                          err ? (float*)(ob + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a, (float*)(ob + o_next));
         if (rc != DR3LK_OK) { cudaStreamSynchronize(st); pyramid_free(p2, false); return rc; }
-        e = cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st);
+        e = out ? cudaSuccess : cudaMemcpyAsync(hp + o_next, dp + o_next, total - o_next, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) { cudaStreamSynchronize(st); pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame: D2H"); }
     }
     e = cudaStreamSynchronize(st);

@@ -48,7 +48,8 @@ struct LKParams {
     LevelTma tma[kTmaLevels];
     int use_tma;           // the descriptors above are valid: stage with cp.async.bulk.tensor instead of cp.async
     const float2* prev_pts;
-    float2* next_pts;
+    float2* next_pts;        // initial estimates (DR3LK_USE_INITIAL_FLOW), device memory
+    float2* next_out;        // results; == next_pts except on the latency path, where it is the mapped pinned mirror of the caller
     uint8_t* status;
     float* err;            // may be null
     uint32_t* stats;       // may be null
@@ -74,7 +75,28 @@ struct Launch {
     cudaStream_t stream;
     cudaError_t err;
     int launches;
+    // Latency path: launch with programmatic stream serialization, so that this kernel's launch overlaps the tail of the
+    // kernel before it in the stream.  Every kernel launched this way starts with grid_dependency_wait(), which returns
+    // once the preceding grid has completed and its writes are visible; without the attribute the wait is a no-op.
+    bool pdl = false;
 };
+
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (An explicit early griddepcontrol.launch_dependents at the top of the pyramid kernels was measured too: 100.4 instead of
+// 94.7 us per call -- the dependents then sit on the SMs spinning in their wait while the primary still needs them.  The
+// implicit trigger at the primary's exit is what is used.)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(const Launch& L, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = L.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // pyramid.cu
 // One level step: reads the source level of n_prev previous-frame images and n_next next-frame images (same size and

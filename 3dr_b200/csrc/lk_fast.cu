@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "dr3lk_internal.cuh"
 
@@ -417,6 +418,9 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     auto pair_of = [&](int f) -> int { return P.uniform_n > 0 ? f / P.uniform_n : __ldg(P.pair_idx + f); };
 
     if (blockIdx.x == 0 && threadIdx.x == 0) P.work_counter[(P.work_epoch & 1) ^ 1] = 0;  // ready for the next launch
+    // everything above is launch-local set-up; the pyramids, the points and the work counter come from the operations before
+    // this kernel in the stream (Launch::pdl)
+    grid_dependency_wait();
     int f = fetch();
     if (f >= P.n_total) return;
     float2 pp = sanitize_point(P.prev_pts[f]);
@@ -690,7 +694,7 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
 
         DR3LK_CHECK((unsigned)f < (unsigned)P.n_total, 8, f);
         if (lane == 0) {
-            P.next_pts[f] = np;
+            P.next_out[f] = np;
             P.status[f] = (uint8_t)status;
             if (want_err) P.err[f] = err;
             if (P.stats) P.stats[f] = (n_iters & 0xffffu) | ((n_templates & 0xffu) << 16) | (err_pass << 24);
@@ -701,25 +705,41 @@ lk_fast_kernel(const __grid_constant__ LKParams P)
     if (!TMA) cp_async_wait<0>();
 }
 
+constexpr int kMaxDevices = 64;
+
 template <typename G, bool TMA>
 bool launch_one(Launch& L, const LKParams& p)
 {
     const size_t smem = (size_t)G::WARPS * G::WARP_WORDS * sizeof(unsigned) + (TMA ? G::WARPS * 16 : 0);
-    L.err = cudaFuncSetAttribute(lk_fast_kernel<G, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (L.err != cudaSuccess) return false;
+    // shared-memory opt-in, SM count and occupancy are per (kernel, device): looked up once, not on every call of the latency path
+    struct PerDevice { int sms = 0, per_sm = 0; };
+    static PerDevice cache[kMaxDevices];
+    static std::mutex cache_mutex;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_fast_kernel<G, TMA>, G::WARPS * 32, smem);
-    if (L.err != cudaSuccess) return false;
+    {
+        std::lock_guard<std::mutex> g(cache_mutex);
+        PerDevice local;
+        PerDevice& c = (dev >= 0 && dev < kMaxDevices) ? cache[dev] : local;
+        if (c.sms == 0) {
+            L.err = cudaFuncSetAttribute(lk_fast_kernel<G, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (L.err != cudaSuccess) return false;
+            int n = 0, o = 0;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            L.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lk_fast_kernel<G, TMA>, G::WARPS * 32, smem);
+            if (L.err != cudaSuccess) return false;
+            c.sms = n; c.per_sm = o;
+        }
+        sms = c.sms; per_sm = c.per_sm;
+    }
     const int want = (p.n_total + G::WARPS - 1) / G::WARPS;
     const int blocks = std::min(want, std::max(1, per_sm) * sms);
     LKParams q = p;
     static const int fetch_max = getenv("DR3LK_FETCH_MAX") ? atoi(getenv("DR3LK_FETCH_MAX")) : 8;
     // reserve several features per atomic only when every warp has at least 64 features to work through
     q.fetch_n = std::max(1, std::min(fetch_max, (int)(p.n_total / (64LL * blocks * G::WARPS))));
-    lk_fast_kernel<G, TMA><<<blocks, G::WARPS * 32, smem, L.stream>>>(q);
-    L.err = cudaGetLastError();
+    L.err = launch_kernel(L, lk_fast_kernel<G, TMA>, dim3(blocks), dim3(G::WARPS * 32), smem, q);
+    if (L.err == cudaSuccess) L.err = cudaGetLastError();
     L.launches++;
     return L.err == cudaSuccess;  // true: the persistent kernel ran and consumed its work counter
 }

@@ -221,7 +221,7 @@ lk_generic_kernel(const __grid_constant__ LKParams P)
     }
 
     if (lane == 0) {
-        P.next_pts[f] = np;
+        P.next_out[f] = np;
         P.status[f] = (uint8_t)status;
         if (want_err) P.err[f] = err;
         if (P.stats) P.stats[f] = (n_iters & 0xffffu) | ((n_templates & 0xffu) << 16) | (err_pass << 24);

@@ -42,6 +42,7 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
     __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
 
+    grid_dependency_wait();  // the source level is the output of the kernel before this one (Launch::pdl)
     const int tid = threadIdx.x;
     const bool set_b = (int)blockIdx.z >= n_a;
     const int img = set_b ? blockIdx.z - n_a : blockIdx.z;
@@ -341,12 +342,12 @@ void launch_pyr_level(Launch& L, const PyrLevelArgs& a)
     PyrSet A{a.prev_src, a.prev_dst, a.prev_src_stride, a.prev_dst_stride};
     PyrSet B{a.next_src, a.next_dst, a.next_src_stride, a.next_dst_stride};
     if (a.down)
-        pyr_level_kernel<true><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                 a.deriv_stride, a.dst_apron_x, a.dst_apron_y, a.src_apron_x, a.src_apron_y);
+        L.err = launch_kernel(L, pyr_level_kernel<true>, grid, dim3(PYR_THREADS), 0, A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv,
+                              a.dpitch, a.deriv_stride, a.dst_apron_x, a.dst_apron_y, a.src_apron_x, a.src_apron_y);
     else
-        pyr_level_kernel<false><<<grid, PYR_THREADS, 0, L.stream>>>(A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
-                                                                  a.deriv_stride, 0, 0, a.src_apron_x, a.src_apron_y);
-    L.err = cudaGetLastError();
+        L.err = launch_kernel(L, pyr_level_kernel<false>, grid, dim3(PYR_THREADS), 0, A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv,
+                              a.dpitch, a.deriv_stride, 0, 0, a.src_apron_x, a.src_apron_y);
+    if (L.err == cudaSuccess) L.err = cudaGetLastError();
     L.launches++;
 }
 

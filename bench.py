@@ -216,6 +216,19 @@ def measure_latency(dr3, ctx):
     for pa in pins:
         pa.free()
     out["what"] = "median wall-clock of the synchronous host-buffer calls (H2D + kernels + D2H + sync inside)"
+    # the same call from compiled C++ through the header shim (3dr_b200/host/call_latency.cpp): no Python binding in the way
+    exe = os.path.join(ROOT, "3dr_b200", "host", "call_latency")
+    if os.path.exists(exe):
+        import subprocess, tempfile
+        with tempfile.TemporaryDirectory() as td:
+            for name, f in (("a.pgm", frames[0]), ("b.pgm", frames[1])):
+                with open(os.path.join(td, name), "wb") as fh:
+                    fh.write(b"P5\n%d %d\n255\n" % (f.shape[1], f.shape[0]))
+                    fh.write(np.ascontiguousarray(f).tobytes())
+            np.savetxt(os.path.join(td, "pts.txt"), few, fmt="%.9g")
+            r = subprocess.run([exe, os.path.join(td, "a.pgm"), os.path.join(td, "b.pgm"), os.path.join(td, "pts.txt"), "300"],
+                               capture_output=True, text=True)
+            out["compiled_cpp_caller"] = json.loads(r.stdout) if r.returncode == 0 else {"failed": (r.stderr or r.stdout)[-300:]}
     return out
 
 

@@ -70,3 +70,23 @@ def test_default_context_device_selection(tmp_path):
     assert subprocess.run(args, env=dict(os.environ, DR3LK_DEVICE="0"), capture_output=True).returncode == 0
     r = subprocess.run(args, env=dict(os.environ, DR3LK_DEVICE="4242"), capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_call_latency_program_gets_identical_results_from_all_three_forms(tmp_path):
+    """3dr_b200/host/call_latency.cpp (the compiled-C++ leg of bench.py's latency block): the plain call with pageable frames, the
+    same call with page-locked frames at the device pitch (direct upload) and the frame-to-frame form must return identical
+    points and status (the program compares them itself; the oracle parity of each form is in test_gpu_lk / test_gpu_next_rows)."""
+    exe = os.path.join(ROOT, "3dr_b200", "host", "call_latency")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = golden_case("c1_default_21x21")["prev_pts"][:400]
+    _write_pgm(tmp_path / "a.pgm", a)
+    _write_pgm(tmp_path / "b.pgm", b)
+    np.savetxt(tmp_path / "pts.txt", pts, fmt="%.9g")
+    r = subprocess.run([exe, str(tmp_path / "a.pgm"), str(tmp_path / "b.pgm"), str(tmp_path / "pts.txt"), "20"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    import json
+    d = json.loads(r.stdout)
+    assert d["identical_results"] is True and d["points"] == 400
+    assert 0 < d["c_abi_call_us_pinned"] and 0 < d["c_abi_call_us_pageable"] and 0 < d["c_abi_track_frame_us_pinned"]
