@@ -14,10 +14,11 @@ namespace dr3lk {
 namespace {
 
 constexpr int TOX = 64;            // output (down-sampled) tile
-constexpr int TOY = 16;
+constexpr int TOY_BATCH = 16;       // output rows per tile: 16 for batches, 8 on the few-frame latency path (twice the blocks,
+constexpr int TOY_FEW = 8;          // about half the dependent work per block)
 constexpr int HX = 16;             // x halo of the source tile: 16 keeps every tile row 16-byte aligned (2 are needed)
 constexpr int SW = 2 * TOX + 2 * HX;   // 160 source bytes per tile row = 10 chunks of 16
-constexpr int SH = 2 * TOY + 4;        // 36 source rows (halo 2)
+// source rows per tile: 2 * TOY + 4 (halo 2) = 36 / 20
 constexpr int SPITCH = SW + 16;        // 176
 constexpr int PYR_THREADS = 256;
 
@@ -34,11 +35,12 @@ struct PyrSet {
     unsigned src_stride, dst_stride;  // bytes between images
 };
 
-template <bool DOWN>
+template <bool DOWN, int TOY>
 __global__ void __launch_bounds__(PYR_THREADS)
 pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int src_aligned, int dst_pitch, int* __restrict__ deriv,
                  int dpitch, unsigned deriv_stride, int apron_x, int apron_y, int src_ax, int src_ay)
 {
+    constexpr int SH = 2 * TOY + 4;
     __shared__ __align__(16) uint8_t tile[SH][SPITCH];
     __shared__ __align__(8) short hrow[DOWN ? SH : 1][DOWN ? TOX : 4];
 
@@ -146,7 +148,7 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
         uint8_t* o = S.dst + (unsigned long long)(unsigned)img * S.dst_stride;
         const int q = tid & 15, oy = tid >> 4;   // 4 outputs per thread, 16 threads per row, 16 rows
         const int gx = blockIdx.x * TOX + 4 * q, gy = blockIdx.y * TOY + oy;
-        if (gx < dw && gy < dh) {
+        if (oy < TOY && gx < dw && gy < dh) {
             // vertical [1 4 6 4 1] on the same 16-bit lanes: 128 + 16 * 4080 < 65536, so (sum + 128) >> 8 is the high byte
             // of each lane and one PRMT packs the four output pixels
             unsigned v01 = 0x00800080u, v23 = 0x00800080u;
@@ -203,7 +205,7 @@ pyr_level_kernel(PyrSet A, PyrSet B, int n_a, int w, int h, int src_pitch, int s
 // Level 0 with its REFLECT_101 apron: one 16-byte destination chunk per thread.  Interior chunks read the source row
 // through aligned 32-bit words realigned with funnel shifts (the caller's rows may have any alignment, e.g. continuous
 // 1241-wide images).
-constexpr int PAD_TX = 32, PAD_TY = 8, PAD_RPT = 4;  // block = 32 chunk columns x 8 rows, 4 rows per thread
+constexpr int PAD_TX = 32, PAD_TY = 8;  // block = 32 chunk columns x 8 rows; PAD_RPT rows per thread (template parameter)
 
 // 16 destination bytes at column x of one row (x is a multiple of 16, -ax <= x): dst[x + i] = srow[reflect101(x + i)].
 // A chunk that lies completely inside the row, or completely in the left / right apron, is 16 CONSECUTIVE source
@@ -234,6 +236,9 @@ __device__ __forceinline__ uint4 pad_chunk(const uint8_t* __restrict__ srow, int
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// PAD_RPT = 4 for batches (loads of four rows in flight per thread: the kernel is HBM-bound there), 1 for the few-frame
+// latency path (four times as many blocks, a quarter of the per-thread chain).
+template <int PAD_RPT>
 __global__ void __launch_bounds__(PAD_TX * PAD_TY)
 pad_level0_kernel(const uint8_t* __restrict__ src_a, const uint8_t* __restrict__ src_b, long long src_pitch, long long src_stride,
                   uint8_t* __restrict__ dst_a, uint8_t* __restrict__ dst_b, int dst_pitch, long long dst_stride, int w, int h, int ax, int ay,
@@ -336,17 +341,25 @@ box_half_kernel(const uint8_t* __restrict__ src, int out_w, int out_h, long long
 void launch_pyr_level(Launch& L, const PyrLevelArgs& a)
 {
     if (L.err != cudaSuccess || a.n_prev + a.n_next <= 0) return;
-    dim3 grid((a.w + 2 * TOX - 1) / (2 * TOX), (a.h + 2 * TOY - 1) / (2 * TOY), a.n_prev + a.n_next);
+    // few images: smaller tiles, so that the stage is spread over more SMs and each block's dependent chain is shorter
+    const bool few = a.n_prev + a.n_next <= 8;
+    const int toy = few ? TOY_FEW : TOY_BATCH;
+    dim3 grid((a.w + 2 * TOX - 1) / (2 * TOX), (a.h + 2 * toy - 1) / (2 * toy), a.n_prev + a.n_next);
     auto al = [](const void* p, size_t x, size_t y) { return ((reinterpret_cast<uintptr_t>(p) | x | y) & 15) == 0; };
     const int aligned = al(a.prev_src, a.src_pitch, a.prev_src_stride) && (a.n_next == 0 || al(a.next_src, a.src_pitch, a.next_src_stride));
     PyrSet A{a.prev_src, a.prev_dst, a.prev_src_stride, a.prev_dst_stride};
     PyrSet B{a.next_src, a.next_dst, a.next_src_stride, a.next_dst_stride};
-    if (a.down)
-        L.err = launch_kernel(L, pyr_level_kernel<true>, grid, dim3(PYR_THREADS), 0, A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv,
-                              a.dpitch, a.deriv_stride, a.dst_apron_x, a.dst_apron_y, a.src_apron_x, a.src_apron_y);
-    else
-        L.err = launch_kernel(L, pyr_level_kernel<false>, grid, dim3(PYR_THREADS), 0, A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv,
-                              a.dpitch, a.deriv_stride, 0, 0, a.src_apron_x, a.src_apron_y);
+    auto go = [&](auto kernel, int ax, int ay) {
+        L.err = launch_kernel(L, kernel, grid, dim3(PYR_THREADS), 0, A, B, a.n_prev, a.w, a.h, a.src_pitch, aligned, a.dst_pitch, a.deriv, a.dpitch,
+                              a.deriv_stride, ax, ay, a.src_apron_x, a.src_apron_y);
+    };
+    if (a.down) {
+        if (few) go(pyr_level_kernel<true, TOY_FEW>, a.dst_apron_x, a.dst_apron_y);
+        else go(pyr_level_kernel<true, TOY_BATCH>, a.dst_apron_x, a.dst_apron_y);
+    } else {
+        if (few) go(pyr_level_kernel<false, TOY_FEW>, 0, 0);
+        else go(pyr_level_kernel<false, TOY_BATCH>, 0, 0);
+    }
     if (L.err == cudaSuccess) L.err = cudaGetLastError();
     L.launches++;
 }
@@ -355,9 +368,14 @@ void launch_pad_level0(Launch& L, const uint8_t* src_a, const uint8_t* src_b, si
                        uint8_t* dst_b, int dst_pitch, size_t dst_stride, int w, int h, int ax, int ay, int n_a, int n_b)
 {
     if (L.err != cudaSuccess || n_a + n_b <= 0) return;
-    dim3 grid((dst_pitch / 16 + PAD_TX - 1) / PAD_TX, (h + 2 * ay + PAD_TY * PAD_RPT - 1) / (PAD_TY * PAD_RPT), n_a + n_b);
-    pad_level0_kernel<<<grid, dim3(PAD_TX, PAD_TY), 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b, dst_pitch,
-                                                  (long long)dst_stride, w, h, ax, ay, n_a);
+    const int rpt = (n_a + n_b <= 8) ? 1 : 4;
+    dim3 grid((dst_pitch / 16 + PAD_TX - 1) / PAD_TX, (h + 2 * ay + PAD_TY * rpt - 1) / (PAD_TY * rpt), n_a + n_b);
+    if (rpt == 1)
+        pad_level0_kernel<1><<<grid, dim3(PAD_TX, PAD_TY), 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b,
+                                                                        dst_pitch, (long long)dst_stride, w, h, ax, ay, n_a);
+    else
+        pad_level0_kernel<4><<<grid, dim3(PAD_TX, PAD_TY), 0, L.stream>>>(src_a, src_b, (long long)src_pitch, (long long)src_stride, dst_a, dst_b,
+                                                                        dst_pitch, (long long)dst_stride, w, h, ax, ay, n_a);
     L.err = cudaGetLastError();
     L.launches++;
 }

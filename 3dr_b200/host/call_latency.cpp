@@ -4,7 +4,11 @@
 // form with the previous frame's pyramid kept on the device (dr3::Pyramid + dr3lk_track_frame).  bench.py --workload kitti
 // runs it and puts the numbers into the `latency` block next to the ones measured through the Python binding.
 //
-// usage: call_latency <prev.pgm> <next.pgm> <points.txt> [calls]      -> one JSON object on stdout
+// With more frames on the command line it also times the frame-to-frame chain over all of them (every
+// frame uploaded once, its pyramid built once and used first as the next and then as the previous frame, surviving points
+// carried forward), frames pageable and pinned.
+//
+// usage: call_latency <prev.pgm> <next.pgm> <points.txt> [calls [more frames.pgm ...]]      -> one JSON object on stdout
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -105,12 +109,63 @@ int main(int argc, char** argv)
             if (rc != DR3LK_OK) throw dr3::Exception(rc, dr3lk_last_error(ctx.get()));
         }, calls);
         const bool same2 = status == ref_status && std::memcmp(next_pts.data(), ref_pts.data(), ref_pts.size() * sizeof(dr3::Point2f)) == 0;
+        // the chain over all frames given: pyramid of frame 0, then one dr3lk_track_frame per new frame
+        double chain_pageable_ms = 0., chain_pinned_ms = 0.;
+        size_t survivors[2] = {0, 0};
+        const int n_frames = argc > 5 ? 2 + (argc - 5) : 0;
+        if (n_frames > 2) {
+            std::vector<Gray> fr(static_cast<size_t>(n_frames));
+            fr[0] = a; fr[1] = b;
+            for (int i = 2; i < n_frames; i++)
+                if (!read_pgm(argv[3 + i], fr[static_cast<size_t>(i)]) || fr[static_cast<size_t>(i)].cols != w || fr[static_cast<size_t>(i)].rows != h)
+                    throw dr3::Exception(DR3LK_E_ARG, "cannot read a chain frame");
+            std::vector<uint8_t*> pin(static_cast<size_t>(n_frames));
+            for (int i = 0; i < n_frames; i++) {
+                pin[static_cast<size_t>(i)] = static_cast<uint8_t*>(dr3lk_host_alloc(step * h));
+                if (!pin[static_cast<size_t>(i)]) throw dr3::Exception(DR3LK_E_CUDA, "dr3lk_host_alloc failed");
+                for (int y = 0; y < h; y++)
+                    std::memcpy(pin[static_cast<size_t>(i)] + y * step, fr[static_cast<size_t>(i)].px.data() + static_cast<size_t>(y) * w, static_cast<size_t>(w));
+            }
+            for (int kind = 0; kind < 2; kind++) {
+                auto chain = [&] {
+                    const uint8_t* f0 = kind ? pin[0] : fr[0].px.data();
+                    const size_t st = kind ? step : static_cast<size_t>(w);
+                    dr3lk_pyramid* cur_pyr = nullptr;
+                    ctx.check(dr3lk_pyramid_create(ctx.get(), f0, w, h, st, 21, 21, 3, &cur_pyr));
+                    std::vector<dr3::Point2f> cur = prev_pts, nxt;
+                    for (int i = 1; i < n_frames; i++) {
+                        nxt.resize(cur.size()); status.resize(cur.size()); err.resize(cur.size());
+                        dr3lk_pyramid* keep = nullptr;
+                        const uint8_t* fi = kind ? pin[static_cast<size_t>(i)] : fr[static_cast<size_t>(i)].px.data();
+                        const int rc = dr3lk_track_frame(ctx.get(), cur_pyr, fi, st, reinterpret_cast<const float*>(cur.data()),
+                                                         reinterpret_cast<float*>(nxt.data()), status.data(), err.data(), static_cast<int>(cur.size()), 21, 21, 3,
+                                                         3, 30, 0.01, 0, 1e-4, 2, &keep);
+                        dr3lk_pyramid_destroy(cur_pyr);
+                        cur_pyr = keep;
+                        if (rc != DR3LK_OK) throw dr3::Exception(rc, dr3lk_last_error(ctx.get()));
+                        size_t k = 0;
+                        for (size_t j = 0; j < cur.size(); j++)
+                            if (status[j]) nxt[k++] = nxt[j];
+                        nxt.resize(k);
+                        cur.swap(nxt);
+                    }
+                    dr3lk_pyramid_destroy(cur_pyr);
+                    survivors[kind] = cur.size();
+                };
+                (kind ? chain_pinned_ms : chain_pageable_ms) = median_us(chain, std::max(10, calls / 10)) / 1e3;
+            }
+            for (uint8_t* m : pin) dr3lk_host_free(m);
+        }
         dr3lk_host_free(ma);
         dr3lk_host_free(mb);
+        const bool ok = same && same2 && survivors[0] == survivors[1];
         std::printf("{\"points\": %zu, \"calls\": %d, \"c_abi_call_us_pageable\": %.2f, \"c_abi_call_us_pinned\": %.2f, "
-                    "\"c_abi_track_frame_us_pinned\": %.2f, \"identical_results\": %s}\n",
-                    prev_pts.size(), calls, pageable, pinned, streaming, (same && same2) ? "true" : "false");
-        return (same && same2) ? 0 : 1;
+                    "\"c_abi_track_frame_us_pinned\": %.2f, ", prev_pts.size(), calls, pageable, pinned, streaming);
+        if (n_frames > 2)
+            std::printf("\"chain_frames\": %d, \"chain_ms_pageable\": %.4f, \"chain_ms_pinned\": %.4f, \"chain_survivors\": %zu, ", n_frames,
+                        chain_pageable_ms, chain_pinned_ms, survivors[1]);
+        std::printf("\"identical_results\": %s}\n", ok ? "true" : "false");
+        return ok ? 0 : 1;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 1;

@@ -229,6 +229,17 @@ def measure_latency(dr3, ctx):
             r = subprocess.run([exe, os.path.join(td, "a.pgm"), os.path.join(td, "b.pgm"), os.path.join(td, "pts.txt"), "300"],
                                capture_output=True, text=True)
             out["compiled_cpp_caller"] = json.loads(r.stdout) if r.returncode == 0 else {"failed": (r.stderr or r.stdout)[-300:]}
+            # C2 from C++: the nine-frame chain with the same starting points as c2_chain_kitti0_9_ms above
+            more = []
+            for i in range(2, 10):
+                more.append(os.path.join(td, "f%d.pgm" % i))
+                with open(more[-1], "wb") as fh:
+                    fh.write(b"P5\n%d %d\n255\n" % (frames[i].shape[1], frames[i].shape[0]))
+                    fh.write(np.ascontiguousarray(frames[i]).tobytes())
+            np.savetxt(os.path.join(td, "many.txt"), many, fmt="%.9g")
+            r = subprocess.run([exe, os.path.join(td, "a.pgm"), os.path.join(td, "b.pgm"), os.path.join(td, "many.txt"), "300"] + more,
+                               capture_output=True, text=True)
+            out["compiled_cpp_chain"] = json.loads(r.stdout) if r.returncode == 0 else {"failed": (r.stderr or r.stdout)[-300:]}
     return out
 
 

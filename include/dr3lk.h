@@ -76,7 +76,7 @@ int dr3lk_profile_read(dr3lk_ctx* ctx, float* lk_ms, int* lk_launches, float* py
  * entry points (dr3lk_calc_optical_flow_pyr_lk, dr3lk_pyramid_create, dr3lk_track_frame) also recognise images that live in
  * page-locked memory (this allocator, cudaHostAlloc, cudaHostRegister) with a row step of exactly (w + 15) / 16 * 16 bytes:
  * such an image goes to the copy engine as it is, without the staging copy into the context's own pinned mirror
- * (KITTI 1241x376 pair from C++: 92 us per call instead of 125 us).  Any other image -- pageable, or pinned at another step -- is
+ * (KITTI 1241x376 pair from C++: 85 us per call instead of 120 us).  Any other image -- pageable, or pinned at another step -- is
  * packed first; results are identical. */
 void* dr3lk_host_alloc(size_t bytes);
 void dr3lk_host_free(void* p);

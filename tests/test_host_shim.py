@@ -84,9 +84,19 @@ def test_call_latency_program_gets_identical_results_from_all_three_forms(tmp_pa
     _write_pgm(tmp_path / "a.pgm", a)
     _write_pgm(tmp_path / "b.pgm", b)
     np.savetxt(tmp_path / "pts.txt", pts, fmt="%.9g")
-    r = subprocess.run([exe, str(tmp_path / "a.pgm"), str(tmp_path / "b.pgm"), str(tmp_path / "pts.txt"), "20"], capture_output=True, text=True)
+    more = []
+    for i in (2, 3):
+        _write_pgm(tmp_path / ("f%d.pgm" % i), load_gray("kitti%d.png" % i))
+        more.append(str(tmp_path / ("f%d.pgm" % i)))
+    r = subprocess.run([exe, str(tmp_path / "a.pgm"), str(tmp_path / "b.pgm"), str(tmp_path / "pts.txt"), "20"] + more, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     import json
     d = json.loads(r.stdout)
     assert d["identical_results"] is True and d["points"] == 400
     assert 0 < d["c_abi_call_us_pinned"] and 0 < d["c_abi_call_us_pageable"] and 0 < d["c_abi_track_frame_us_pinned"]
+    # the chain kitti0 -> 1 -> 2 -> 3, survivors carried forward: as many as the oracle keeps
+    cur = pts
+    for i in range(3):
+        p, s, _ = oracle.calc_optical_flow_pyr_lk(load_gray("kitti%d.png" % i), load_gray("kitti%d.png" % (i + 1)), cur)
+        cur = p[s == 1]
+    assert d["chain_frames"] == 4 and d["chain_survivors"] == len(cur) and d["chain_ms_pinned"] > 0
