@@ -29,7 +29,7 @@ MAX_LEVELS = 16
 # every symbol include/dr3lk.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "dr3lk_create", "dr3lk_destroy", "dr3lk_last_error", "dr3lk_set_stream", "dr3lk_synchronize", "dr3lk_launch_count",
-    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_debug_check_read", "dr3lk_debug_set_fast_arc", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
+    "dr3lk_set_profiling", "dr3lk_profile_read", "dr3lk_debug_check_read", "dr3lk_debug_set_fast_arc", "dr3lk_host_alloc", "dr3lk_host_free", "dr3lk_host_register", "dr3lk_host_unregister", "dr3lk_box_pyramid", "dr3lk_box_pyramid_device",
     "dr3lk_calc_optical_flow_pyr_lk", "dr3lk_track_batch", "dr3lk_track_batch_host", "dr3lk_lk_level_sizes",
     "dr3lk_build_lk_pyramid", "dr3lk_pyramid_create", "dr3lk_pyramid_destroy", "dr3lk_pyramid_levels",
     "dr3lk_calc_optical_flow_pyr_lk_cached", "dr3lk_track_frame", "dr3lk_filter_tracks", "dr3lk_fast_detect", "dr3lk_score_fundamental",
@@ -78,6 +78,8 @@ def lib():
     L.dr3lk_host_alloc.restype = c_void_p
     L.dr3lk_host_free.argtypes = [c_void_p]
     L.dr3lk_host_free.restype = None
+    L.dr3lk_host_register.argtypes = [c_void_p, c_size_t]
+    L.dr3lk_host_unregister.argtypes = [c_void_p]
     L.dr3lk_box_pyramid.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, P(c_void_p), c_int]
     L.dr3lk_box_pyramid_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int, c_int, P(c_void_p), c_int]
     lk_tail = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_double]  # win_w .. min_eig_threshold
@@ -140,6 +142,19 @@ def _gray(img):
     if img.strides[1] != 1 or img.strides[0] < img.shape[1]:
         img = np.ascontiguousarray(img)
     return img
+
+
+def host_register(arr):
+    """Page-locks the memory of an existing C-contiguous numpy array (dr3lk_host_register); pair with host_unregister(arr)."""
+    rc = lib().dr3lk_host_register(arr.ctypes.data, arr.nbytes)
+    if rc != 0:
+        raise Dr3lkError(rc, "dr3lk_host_register failed")
+
+
+def host_unregister(arr):
+    rc = lib().dr3lk_host_unregister(arr.ctypes.data)
+    if rc != 0:
+        raise Dr3lkError(rc, "dr3lk_host_unregister failed")
 
 
 class PinnedArray:

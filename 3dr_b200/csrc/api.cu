@@ -591,6 +591,20 @@ void* dr3lk_host_alloc(size_t bytes)
 
 void dr3lk_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+int dr3lk_host_register(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return DR3LK_E_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return DR3LK_E_CUDA; }
+    return DR3LK_OK;
+}
+
+int dr3lk_host_unregister(void* p)
+{
+    if (!p) return DR3LK_E_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return DR3LK_E_CUDA; }
+    return DR3LK_OK;
+}
+
 int dr3lk_lk_level_sizes(int w, int h, int win_w, int win_h, int max_level, int* ws, int* hs)
 {
     // buildOpticalFlowPyramid: level l+1 = ((w+1)/2, (h+1)/2); stop when the NEXT level would not exceed the window
@@ -761,24 +775,29 @@ static uint8_t* mapped_alias(void* host, int n)
     return (uint8_t*)d;
 }
 
-// True when the image can go to the copy engine as it is: page-locked host memory (dr3lk_host_alloc, cudaHostAlloc,
-// cudaHostRegister) whose rows already sit at the device pitch, so that the upload is ONE contiguous copy and the staging
-// memcpy into the context's pinned mirror (~15 us per KITTI frame) is skipped.  Pinned rows at any other step are packed like
+// The device row pitch at which an image can go to the copy engine as it is, or 0: page-locked host memory (dr3lk_host_alloc,
+// cudaHostAlloc, cudaHostRegister) whose rows are either continuous (step == w, the usual cv::Mat) or sit at the 16-byte
+// aligned pitch -- then the upload is ONE contiguous copy and the staging memcpy into the context's pinned mirror (~15 us per
+// KITTI frame) is skipped; the level-0 apron copy reads rows of any alignment.  Pinned rows at any other step are packed like
 // pageable ones: a 2-D DMA of 1241-byte rows was measured 36 us per call SLOWER than packing (profiles/README.md, round 2).
-static bool direct_upload(const void* img, size_t step, int pitch0)
+static size_t direct_pitch(const void* img, size_t step, int w, int pitch0)
 {
-    if (step != (size_t)pitch0) return false;
+    if (step != (size_t)pitch0 && step != (size_t)w) return 0;
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, img) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    if (cudaPointerGetAttributes(&at, img) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeHost ? step : 0;
 }
 static size_t direct_bytes(size_t step, int w, int h) { return (size_t)(h - 1) * step + (size_t)w; }  // never past the last pixel
 
-// Level-0 upload of one image (rows of w bytes at `step`) to device rows at pitch0.  The caller synchronises the stream
-// before it returns to its own caller, so the source only has to stay valid for the duration of the call.
-static cudaError_t upload_image(uint8_t* dev, uint8_t* stage, int pitch0, const uint8_t* img, size_t step, int w, int h, cudaStream_t st)
+// Level-0 upload of one image (rows of w bytes at `step`); *dev_pitch receives the row pitch of the device copy (the image's own
+// step when it went directly, else pitch0).  The caller synchronises the stream before it returns to its own caller, so the
+// source only has to stay valid for the duration of the call.
+static cudaError_t upload_image(uint8_t* dev, uint8_t* stage, int pitch0, const uint8_t* img, size_t step, int w, int h, cudaStream_t st,
+                                size_t* dev_pitch)
 {
-    if (direct_upload(img, step, pitch0)) return cudaMemcpyAsync(dev, img, direct_bytes(step, w, h), cudaMemcpyHostToDevice, st);
+    const size_t direct = direct_pitch(img, step, w, pitch0);
+    *dev_pitch = direct ? direct : (size_t)pitch0;
+    if (direct) return cudaMemcpyAsync(dev, img, direct_bytes(step, w, h), cudaMemcpyHostToDevice, st);
     for (int y = 0; y < h; y++) memcpy(stage + (size_t)y * pitch0, img + (size_t)y * step, (size_t)w);
     return cudaMemcpyAsync(dev, stage, (size_t)pitch0 * h, cudaMemcpyHostToDevice, st);
 }
@@ -812,9 +831,16 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     // The previous image crosses PCIe while the host is still packing the next one: two copies, the first one hidden behind
     // the second memcpy (the staging memcpy of ~0.5 MB per image is as long as its DMA)
-    // (pinned images whose rows sit at the device pitch skip the packing altogether)
-    CU_TRY(ctx, upload_image(dp, hp, pitch0, prev, prev_step, w, h, st));
-    const bool next_pinned = direct_upload(next, next_step, pitch0);
+    // (pinned images, continuous or at the aligned pitch, skip the packing altogether; both frames share one device pitch)
+    const size_t dp_prev = direct_pitch(prev, prev_step, w, pitch0), dp_next = direct_pitch(next, next_step, w, pitch0);
+    const size_t pitch = (dp_prev && dp_prev == dp_next) ? dp_prev : (size_t)pitch0;
+    const bool prev_pinned = dp_prev == pitch, next_pinned = dp_next == pitch;
+    if (prev_pinned) {
+        CU_TRY(ctx, cudaMemcpyAsync(dp, prev, direct_bytes(prev_step, w, h), cudaMemcpyHostToDevice, st));
+    } else {
+        for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
+        CU_TRY(ctx, cudaMemcpyAsync(dp, hp, img_bytes, cudaMemcpyHostToDevice, st));
+    }
     if (next_pinned) CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, next, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st));
     else for (int y = 0; y < h; y++) memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
     memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
@@ -831,7 +857,7 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     if (!mapped_pts) CU_TRY(ctx, cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st));
     const uint8_t* const pb = mapped_pts ? out : dp;
     // (the device copy of the offsets is only read for batches with differing point counts)
-    rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch0, img_bytes, 1, (const float*)(pb + o_prev), (float*)(pb + o_next),
+    rc = track_batch_device(ctx, W, st, dp, dp + img_bytes, w, h, pitch, img_bytes, 1, (const float*)(pb + o_prev), (float*)(pb + o_next),
                             ob + o_status, err ? (float*)(ob + o_err) : nullptr, offs, (const int*)(dp + o_offs), n, nullptr, a,
                             (float*)(ob + o_next));
     if (rc != DR3LK_OK) return rc;
@@ -1213,8 +1239,9 @@ int dr3lk_pyramid_create(dr3lk_ctx* ctx, const uint8_t* img, int w, int h, size_
     if (e != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, e, "pyramid_create: allocation"); }
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     Launch L{st, cudaSuccess, 0};
-    L.err = upload_image((uint8_t*)ctx->ws.lvl0_prev.p, hp, pitch0, img, step, w, h, st);
-    pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, pitch0, st, L);
+    size_t pitch = 0;
+    L.err = upload_image((uint8_t*)ctx->ws.lvl0_prev.p, hp, pitch0, img, step, w, h, st, &pitch);
+    pyramid_enqueue(ctx, p, (const uint8_t*)ctx->ws.lvl0_prev.p, pitch, st, L);
     // the pinned staging buffer is reused by the next call: wait for the upload
     if (L.err == cudaSuccess) L.err = cudaStreamSynchronize(st);
     if (L.err != cudaSuccess) { pyramid_free(p, false); return fail_cuda(ctx, L.err, "pyramid_create"); }
@@ -1325,8 +1352,9 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
     if (e != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, e, "track_frame: allocation"); }
     uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    // a pinned image at the device pitch goes to the copy engine as it is; any other is packed in front of the points (one copy for both)
-    const bool img_pinned = direct_upload(next_img, next_step, pitch0);
+    // a pinned image (continuous, or at the aligned pitch) goes to the copy engine as it is; any other is packed in front of the points
+    const size_t pitch_direct = direct_pitch(next_img, next_step, w, pitch0);
+    const bool img_pinned = pitch_direct != 0;
     Launch L{st, cudaSuccess, 0};
     if (img_pinned) L.err = cudaMemcpyAsync(dp, next_img, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st);
     else for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, next_img + (size_t)y * next_step, (size_t)w);
@@ -1343,7 +1371,7 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
     const bool mapped_pts = img_pinned && out && mapped_points_enabled();                    // no second copy in front of the kernels for a few hundred bytes
     if (L.err == cudaSuccess && in_bytes > in_from && !mapped_pts)
         L.err = cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st);
-    pyramid_enqueue(ctx, p2, dp, pitch0, st, L);
+    pyramid_enqueue(ctx, p2, dp, img_pinned ? pitch_direct : (size_t)pitch0, st, L);
     if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
     if (n > 0) {
         LKParams lk;

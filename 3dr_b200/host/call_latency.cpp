@@ -1,6 +1,6 @@
 // Per-call latency of the reference's call pattern as a compiled C++ caller sees it (no Python binding in the way):
 // dr3::calcOpticalFlowPyrLK(prev, next, ...) on one frame pair, once with the frames in ordinary (pageable) memory and once
-// in page-locked memory with rows at the device pitch (dr3lk_host_alloc), and the frame-to-frame
+// in page-locked memory (dr3lk_host_alloc; rows at the aligned pitch and continuous), and the frame-to-frame
 // form with the previous frame's pyramid kept on the device (dr3::Pyramid + dr3lk_track_frame).  bench.py --workload kitti
 // runs it and puts the numbers into the `latency` block next to the ones measured through the Python binding.
 //
@@ -94,8 +94,20 @@ int main(int argc, char** argv)
         }
         const dr3::Image qa(ma, w, h, step), qb(mb, w, h, step);
         const double pinned = median_us([&] { dr3::calcOpticalFlowPyrLK(qa, qb, prev_pts, next_pts, status, err); }, calls);
-        const bool same = next_pts.size() == ref_pts.size() && status == ref_status &&
-                          std::memcmp(next_pts.data(), ref_pts.data(), ref_pts.size() * sizeof(dr3::Point2f)) == 0;
+        bool same = next_pts.size() == ref_pts.size() && status == ref_status &&
+                    std::memcmp(next_pts.data(), ref_pts.data(), ref_pts.size() * sizeof(dr3::Point2f)) == 0;
+
+        // ... and as CONTINUOUS page-locked images (row step == width: what cv::Mat(rows, cols, CV_8U, pinned_ptr) is)
+        uint8_t* ca = static_cast<uint8_t*>(dr3lk_host_alloc(a.px.size()));
+        uint8_t* cb = static_cast<uint8_t*>(dr3lk_host_alloc(b.px.size()));
+        if (!ca || !cb) throw dr3::Exception(DR3LK_E_CUDA, "dr3lk_host_alloc failed");
+        std::memcpy(ca, a.px.data(), a.px.size());
+        std::memcpy(cb, b.px.data(), b.px.size());
+        const dr3::Image ra(ca, w, h, static_cast<size_t>(w)), rb(cb, w, h, static_cast<size_t>(w));
+        const double pinned_cont = median_us([&] { dr3::calcOpticalFlowPyrLK(ra, rb, prev_pts, next_pts, status, err); }, calls);
+        same = same && status == ref_status && std::memcmp(next_pts.data(), ref_pts.data(), ref_pts.size() * sizeof(dr3::Point2f)) == 0;
+        dr3lk_host_free(ca);
+        dr3lk_host_free(cb);
 
         // frame-to-frame form: the previous frame's pyramid is on the device, one upload per call
         dr3::Context& ctx = dr3::Context::thread_default();
@@ -160,7 +172,8 @@ int main(int argc, char** argv)
         dr3lk_host_free(mb);
         const bool ok = same && same2 && survivors[0] == survivors[1];
         std::printf("{\"points\": %zu, \"calls\": %d, \"c_abi_call_us_pageable\": %.2f, \"c_abi_call_us_pinned\": %.2f, "
-                    "\"c_abi_track_frame_us_pinned\": %.2f, ", prev_pts.size(), calls, pageable, pinned, streaming);
+                    "\"c_abi_call_us_pinned_continuous\": %.2f, \"c_abi_track_frame_us_pinned\": %.2f, ", prev_pts.size(), calls, pageable, pinned,
+                    pinned_cont, streaming);
         if (n_frames > 2)
             std::printf("\"chain_frames\": %d, \"chain_ms_pageable\": %.4f, \"chain_ms_pinned\": %.4f, \"chain_survivors\": %zu, ", n_frames,
                         chain_pageable_ms, chain_pinned_ms, survivors[1]);

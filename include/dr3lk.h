@@ -74,12 +74,18 @@ int dr3lk_set_profiling(dr3lk_ctx* ctx, int on);
 int dr3lk_profile_read(dr3lk_ctx* ctx, float* lk_ms, int* lk_launches, float* pyramid_ms, int* pyramid_builds);
 /* Pinned host memory for callers that want the host-buffer entry points to overlap copies with compute.  The single-pair
  * entry points (dr3lk_calc_optical_flow_pyr_lk, dr3lk_pyramid_create, dr3lk_track_frame) also recognise images that live in
- * page-locked memory (this allocator, cudaHostAlloc, cudaHostRegister) with a row step of exactly (w + 15) / 16 * 16 bytes:
- * such an image goes to the copy engine as it is, without the staging copy into the context's own pinned mirror
+ * page-locked memory (this allocator, dr3lk_host_register, cudaHostAlloc, cudaHostRegister) whose rows are continuous
+ * (step == w, the usual cv::Mat) or sit at the aligned pitch (w + 15) / 16 * 16 -- for the two-image call both frames at the
+ * same step: such an image goes to the copy engine as it is, without the staging copy into the context's own pinned mirror
  * (KITTI 1241x376 pair from C++: 85 us per call instead of 120 us).  Any other image -- pageable, or pinned at another step -- is
  * packed first; results are identical. */
 void* dr3lk_host_alloc(size_t bytes);
 void dr3lk_host_free(void* p);
+/* Page-locks memory the caller already owns (cudaHostRegister / cudaHostUnregister), e.g. the data of an existing continuous
+ * cv::Mat or a camera ring buffer: register once when the buffer is created (it costs a fraction of a millisecond), unregister
+ * before freeing it.  Registered images take the same direct path as dr3lk_host_alloc memory. */
+int dr3lk_host_register(void* p, size_t bytes);
+int dr3lk_host_unregister(void* p);
 
 /* ---- (2) box pyramid: utils::create_img_pyramid, reference src/utils.cpp:421-430 ------------------ */
 /* Host buffers.  img: h rows of `step` bytes, CV_8UC1.  out_levels[l-1] receives level l (l = 1..n_levels-1),

@@ -250,9 +250,9 @@ def test_pooled_pyramid_buffers_changing_roles_stay_correct(ctx, dr3):
 
 
 def test_page_locked_images_skip_the_staging_copy_and_change_nothing(ctx, dr3):
-    """Images in page-locked memory (dr3lk_host_alloc) whose rows sit at the device pitch (width rounded up to 16) are handed
-    to the copy engine directly instead of being packed into the context's mirror; pinned images at any other step are packed
-    like pageable ones.  Whole frames and a strided ROI inside a pinned frame, through the two-image call,
+    """Images in page-locked memory (dr3lk_host_alloc) whose rows are continuous or sit at the aligned device pitch (width
+    rounded up to 16) are handed to the copy engine directly instead of being packed into the context's mirror; pinned images
+    at any other step are packed like pageable ones.  Whole frames and a strided ROI inside a pinned frame, through the two-image call,
     dr3lk_pyramid_create and dr3lk_track_frame -- results identical to pageable inputs and to the oracle."""
     frames = [load_gray("kitti%d.png" % i) for i in range(3)]
     h, w = frames[0].shape
@@ -280,6 +280,39 @@ def test_page_locked_images_skip_the_staging_copy_and_change_nothing(ctx, dr3):
     got = ctx.calc_optical_flow_pyr_lk(r0, r1, q)
     exp = oracle.calc_optical_flow_pyr_lk(np.ascontiguousarray(r0), np.ascontiguousarray(r1), q)
     assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp))
+    # CONTINUOUS pinned frames (row step == width, the usual cv::Mat): also direct, at an unaligned device pitch -- the odd
+    # 1241-wide pair and the even 1240-wide one; one side continuous and the other at the aligned pitch -> both are packed
+    odd = [load_gray("kitti_000000.png"), load_gray("kitti_000001.png")]
+    assert odd[0].shape[1] == 1241
+    for fa, fb in [(frames[0], frames[1]), (odd[0], odd[1])]:
+        ca, cb = dr3.PinnedArray(fa.shape, np.uint8), dr3.PinnedArray(fb.shape, np.uint8)
+        ca.array[...] = fa; cb.array[...] = fb
+        exp = oracle.calc_optical_flow_pyr_lk(fa, fb, pts)
+        for a_img, b_img in [(ca.array, cb.array), (ca.array, fb), (fa, cb.array)]:
+            got = ctx.calc_optical_flow_pyr_lk(a_img, b_img, pts)
+            assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp))
+        # the reference's literal parameters (30x30 window) and a window without a specialised kernel (generic path reads level 0 raw)
+        for win, ml in [((30, 30), 4), ((13, 17), 2)]:
+            got = ctx.calc_optical_flow_pyr_lk(ca.array, cb.array, pts[:500], None, win, ml, (3, 30, 0.01), 0)
+            exp2 = oracle.calc_optical_flow_pyr_lk(fa, fb, pts[:500], None, win, ml, (3, 30, 0.01), 0)
+            assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp2)), (win, fa.shape)
+        if fa.shape == frames[0].shape:
+            got = ctx.calc_optical_flow_pyr_lk(ca.array, pf[1], pts)        # continuous + aligned pitch: mixed, packed
+            assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, exp))
+        pc = dr3.Pyramid(ctx, ca.array, (21, 21), 3)
+        p_, s_, e_, _ = ctx.track_frame(pc, cb.array, pts, keep_next=0)
+        assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip((p_, s_, e_), exp))
+        pc.close(); ca.free(); cb.free()
+    # memory the caller already owns, page-locked in place (dr3lk_host_register): same path, same results; and back to pageable
+    ra, rb = frames[0].copy(), frames[1].copy()
+    dr3.host_register(ra); dr3.host_register(rb)
+    got = ctx.calc_optical_flow_pyr_lk(ra, rb, pts)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc))
+    dr3.host_unregister(ra); dr3.host_unregister(rb)
+    got = ctx.calc_optical_flow_pyr_lk(ra, rb, pts)
+    assert all(np.array_equal(a.view(np.uint8), c.view(np.uint8)) for a, c in zip(got, orc))
+    with pytest.raises(dr3.Dr3lkError):
+        dr3.host_unregister(ra)                                  # not registered any more
     # cached pyramids and the streaming call
     prev = dr3.Pyramid(ctx, pf[0], (21, 21), 3)
     p, s, e, nxt = ctx.track_frame(prev, pf[1], pts, keep_next=2)
