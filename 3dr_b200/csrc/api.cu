@@ -775,14 +775,18 @@ static uint8_t* mapped_alias(void* host, int n)
     return (uint8_t*)d;
 }
 
-// The device row pitch at which an image can go to the copy engine as it is, or 0: page-locked host memory (dr3lk_host_alloc,
-// cudaHostAlloc, cudaHostRegister) whose rows are either continuous (step == w, the usual cv::Mat) or sit at the 16-byte
-// aligned pitch -- then the upload is ONE contiguous copy and the staging memcpy into the context's pinned mirror (~15 us per
-// KITTI frame) is skipped; the level-0 apron copy reads rows of any alignment.  Pinned rows at any other step are packed like
-// pageable ones: a 2-D DMA of 1241-byte rows was measured 36 us per call SLOWER than packing (profiles/README.md, round 2).
+// The device row pitch at which an image is uploaded as it is -- ONE contiguous copy at its own row step, no packing into the
+// context's pinned mirror -- or 0.  That is every image whose rows are continuous (step == w, the usual cv::Mat) or sit at
+// the 16-byte aligned pitch; the level-0 apron copy reads rows of any alignment.  From page-locked memory (dr3lk_host_alloc,
+// dr3lk_host_register, cudaHostAlloc) the copy is an asynchronous DMA: 85 us per KITTI call.  From pageable memory
+// cudaMemcpyAsync stages through the driver's own pinned buffers and returns when the source has been consumed: 112 us,
+// against 120 us for packing it ourselves (2 x 15 us of memcpy on the critical path).  Rows at any other step (ROIs) are packed:
+// a 2-D DMA of 1241-byte rows into an aligned pitch was measured 36 us per call SLOWER than packing.
 static size_t direct_pitch(const void* img, size_t step, int w, int pitch0)
 {
     if (step != (size_t)pitch0 && step != (size_t)w) return 0;
+    static const bool pack_pageable = getenv("DR3LK_PACK_PAGEABLE") != nullptr;  // measurement knob: the old behaviour
+    if (!pack_pageable) return step;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, img) != cudaSuccess) { cudaGetLastError(); return 0; }
     return at.type == cudaMemoryTypeHost ? step : 0;
@@ -829,19 +833,19 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     CU_TRY(ctx, ctx->pinned.reserve(total));
     uint8_t* dp = (uint8_t*)W.lvl0_prev.p;
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
-    // The previous image crosses PCIe while the host is still packing the next one: two copies, the first one hidden behind
-    // the second memcpy (the staging memcpy of ~0.5 MB per image is as long as its DMA)
-    // (pinned images, continuous or at the aligned pitch, skip the packing altogether; both frames share one device pitch)
+    // Images that are continuous or at the aligned pitch are uploaded as they are (direct_pitch; both frames share one device
+    // pitch).  Any other is packed into the mirror first; then the previous image crosses PCIe while the host is still packing
+    // the next one (the staging memcpy of ~0.5 MB per image is as long as its DMA).
     const size_t dp_prev = direct_pitch(prev, prev_step, w, pitch0), dp_next = direct_pitch(next, next_step, w, pitch0);
     const size_t pitch = (dp_prev && dp_prev == dp_next) ? dp_prev : (size_t)pitch0;
-    const bool prev_pinned = dp_prev == pitch, next_pinned = dp_next == pitch;
-    if (prev_pinned) {
+    const bool prev_direct = dp_prev == pitch, next_direct = dp_next == pitch;
+    if (prev_direct) {
         CU_TRY(ctx, cudaMemcpyAsync(dp, prev, direct_bytes(prev_step, w, h), cudaMemcpyHostToDevice, st));
     } else {
         for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, prev + (size_t)y * prev_step, (size_t)w);
         CU_TRY(ctx, cudaMemcpyAsync(dp, hp, img_bytes, cudaMemcpyHostToDevice, st));
     }
-    if (next_pinned) CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, next, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st));
+    if (next_direct) CU_TRY(ctx, cudaMemcpyAsync(dp + img_bytes, next, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st));
     else for (int y = 0; y < h; y++) memcpy(hp + img_bytes + (size_t)y * pitch0, next + (size_t)y * next_step, (size_t)w);
     memcpy(hp + o_prev, prev_pts, 8 * (size_t)n);
     const int offs[2] = {0, n};
@@ -850,10 +854,10 @@ int dr3lk_calc_optical_flow_pyr_lk(dr3lk_ctx* ctx, const uint8_t* prev, size_t p
     if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
     uint8_t* const out = mapped_alias(hp, n);  // results straight into the pinned mirror, or ...
     uint8_t* const ob = out ? out : dp;
-    // The points ride behind the next image when it was packed.  When it was not (pinned frames), a third copy would sit in
+    // The points ride behind the next image when it was packed.  When it was not, a third copy would sit in
     // front of the kernels for a few hundred bytes: the LK kernel reads the points from the mapped mirror instead.
-    const bool mapped_pts = next_pinned && out && mapped_points_enabled();
-    const size_t in_from = next_pinned ? o_prev : img_bytes;
+    const bool mapped_pts = next_direct && out && mapped_points_enabled();
+    const size_t in_from = next_direct ? o_prev : img_bytes;
     if (!mapped_pts) CU_TRY(ctx, cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st));
     const uint8_t* const pb = mapped_pts ? out : dp;
     // (the device copy of the offsets is only read for batches with differing point counts)
@@ -1354,9 +1358,9 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
     uint8_t* hp = (uint8_t*)ctx->pinned.p;
     // a pinned image (continuous, or at the aligned pitch) goes to the copy engine as it is; any other is packed in front of the points
     const size_t pitch_direct = direct_pitch(next_img, next_step, w, pitch0);
-    const bool img_pinned = pitch_direct != 0;
+    const bool img_direct = pitch_direct != 0;
     Launch L{st, cudaSuccess, 0};
-    if (img_pinned) L.err = cudaMemcpyAsync(dp, next_img, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st);
+    if (img_direct) L.err = cudaMemcpyAsync(dp, next_img, direct_bytes(next_step, w, h), cudaMemcpyHostToDevice, st);
     else for (int y = 0; y < h; y++) memcpy(hp + (size_t)y * pitch0, next_img + (size_t)y * next_step, (size_t)w);
     const int offs[2] = {0, n};
     size_t in_bytes = img_block;
@@ -1366,12 +1370,12 @@ int dr3lk_track_frame(dr3lk_ctx* ctx, const dr3lk_pyramid* prev, const uint8_t* 
         in_bytes = o_next;
         if (flags & DR3LK_USE_INITIAL_FLOW) { memcpy(hp + o_next, next_pts, 8 * (size_t)n); in_bytes = o_next + 8 * (size_t)n; }
     }
-    const size_t in_from = img_pinned ? o_prev : 0;
+    const size_t in_from = img_direct ? o_prev : 0;
     uint8_t* const out = n > 0 ? mapped_alias(hp, n) : nullptr;  // results (and, with a pinned image, the points) through the mapped mirror
-    const bool mapped_pts = img_pinned && out && mapped_points_enabled();                    // no second copy in front of the kernels for a few hundred bytes
+    const bool mapped_pts = img_direct && out && mapped_points_enabled();                    // no second copy in front of the kernels for a few hundred bytes
     if (L.err == cudaSuccess && in_bytes > in_from && !mapped_pts)
         L.err = cudaMemcpyAsync(dp + in_from, hp + in_from, in_bytes - in_from, cudaMemcpyHostToDevice, st);
-    pyramid_enqueue(ctx, p2, dp, img_pinned ? pitch_direct : (size_t)pitch0, st, L);
+    pyramid_enqueue(ctx, p2, dp, img_direct ? pitch_direct : (size_t)pitch0, st, L);
     if (L.err != cudaSuccess) { pyramid_free(p2, false); return fail_cuda(ctx, L.err, "track_frame: pyramid of the new frame"); }
     if (n > 0) {
         LKParams lk;

@@ -73,12 +73,12 @@ uint64_t dr3lk_launch_count(const dr3lk_ctx* ctx);
 int dr3lk_set_profiling(dr3lk_ctx* ctx, int on);
 int dr3lk_profile_read(dr3lk_ctx* ctx, float* lk_ms, int* lk_launches, float* pyramid_ms, int* pyramid_builds);
 /* Pinned host memory for callers that want the host-buffer entry points to overlap copies with compute.  The single-pair
- * entry points (dr3lk_calc_optical_flow_pyr_lk, dr3lk_pyramid_create, dr3lk_track_frame) also recognise images that live in
- * page-locked memory (this allocator, dr3lk_host_register, cudaHostAlloc, cudaHostRegister) whose rows are continuous
- * (step == w, the usual cv::Mat) or sit at the aligned pitch (w + 15) / 16 * 16 -- for the two-image call both frames at the
- * same step: such an image goes to the copy engine as it is, without the staging copy into the context's own pinned mirror
- * (KITTI 1241x376 pair from C++: 85 us per call instead of 120 us).  Any other image -- pageable, or pinned at another step -- is
- * packed first; results are identical. */
+ * entry points (dr3lk_calc_optical_flow_pyr_lk, dr3lk_pyramid_create, dr3lk_track_frame) upload an image as it is -- one
+ * contiguous copy, no packing into the context's own pinned mirror -- when its rows are continuous (step == w, the usual
+ * cv::Mat) or sit at the aligned pitch (w + 15) / 16 * 16 (for the two-image call: both frames at the same step).  From
+ * page-locked memory (this allocator, dr3lk_host_register, cudaHostAlloc, cudaHostRegister) that copy is an asynchronous DMA:
+ * 85 us per call on a KITTI 1241x376 pair from C++; from pageable memory the driver stages it: 114 us.  Rows at any other
+ * step (ROIs) are packed first (120 us); results are identical in all three cases. */
 void* dr3lk_host_alloc(size_t bytes);
 void dr3lk_host_free(void* p);
 /* Page-locks memory the caller already owns (cudaHostRegister / cudaHostUnregister), e.g. the data of an existing continuous
