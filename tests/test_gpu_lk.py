@@ -326,3 +326,59 @@ def test_lk_non_finite_and_huge_points_are_lost_not_fatal(ctx, dr3, win, ml):
         assert np.array_equal(got[1], exp[1])
         ok = got[1] == 1
         assert np.array_equal(got[0][ok].view(np.uint32), exp[0][ok].view(np.uint32)) and np.array_equal(got[2][ok], exp[2][ok])
+
+
+def test_single_call_with_more_points_than_the_mapped_output_limit(ctx, dr3):
+    """Above 16384 points the single-pair calls copy the results back instead of letting the LK kernel write them into the
+    mapped pinned mirror: 20000 points through the two-image call and the streaming call, bit-exact against the oracle."""
+    a, b = load_gray("kitti0.png"), load_gray("kitti1.png")
+    pts = random_points(np.random.default_rng(20000), a.shape[1], a.shape[0], 20000, margin=10)
+    exp = oracle.calc_optical_flow_pyr_lk(a, b, pts)
+    _assert_bit_exact(ctx.calc_optical_flow_pyr_lk(a, b, pts), exp, "20000 points")
+    init = pts + np.float32(0.5)
+    exp2 = oracle.calc_optical_flow_pyr_lk(a, b, pts, init, (21, 21), 3, (3, 30, 0.01), dr3.USE_INITIAL_FLOW)
+    prev = dr3.Pyramid(ctx, a, (21, 21), 3)
+    p, s, e, _ = ctx.track_frame(prev, b, pts, init, 3, (3, 30, 0.01), dr3.USE_INITIAL_FLOW, keep_next=0)
+    _assert_bit_exact((p, s, e), exp2, "20000 points, streaming, initial flow")
+    prev.close()
+
+
+def test_latency_measures_switched_off_give_the_same_results():
+    """The single-pair latency measures (programmatic dependent launches, results written into the mapped pinned mirror, points
+    read from it, direct upload of continuous frames) each have a knob that restores the plain path (tools/latency_ab.sh).
+    The knobs are read once per process, so the plain paths run in a child process: golden cases, pinned and pageable frames,
+    the streaming call -- bit-exact against the oracle."""
+    import os
+    import subprocess
+    import sys
+    from _common import ROOT
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle
+from _common import golden_case, load_gray, random_points
+m = importlib.import_module("3dr_b200")
+def same(got, exp):
+    return all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(got, exp))
+with m.Context(0) as ctx:
+    for case in ("c1_default_21x21", "c1_reference_30x30_initflow", "oddwidth_21x21"):
+        g = golden_case(case)
+        a, b = load_gray(g["prev"]), load_gray(g["next"])
+        args = (a, b, g["prev_pts"], g["init"], g["win"], g["max_level"], g["crit"], g["flags"])
+        exp = oracle.calc_optical_flow_pyr_lk(*args)
+        for rep in range(5):
+            assert same(ctx.calc_optical_flow_pyr_lk(*args), exp), case
+        pa, pb = m.PinnedArray(a.shape, np.uint8), m.PinnedArray(b.shape, np.uint8)
+        pa.array[...] = a; pb.array[...] = b
+        assert same(ctx.calc_optical_flow_pyr_lk(pa.array, pb.array, *args[2:]), exp), case
+        if tuple(g["win"]) == (21, 21):
+            prev = m.Pyramid(ctx, pa.array, (21, 21), g["max_level"])
+            p, s, e, _ = ctx.track_frame(prev, pb.array, g["prev_pts"], g["init"], g["max_level"], g["crit"], g["flags"], keep_next=0)
+            assert same((p, s, e), exp), case
+            prev.close()
+        pa.free(); pb.free()
+print("plain ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, DR3LK_NO_PDL="1", DR3LK_NO_DIRECT_OUT="1", DR3LK_NO_MAPPED_PTS="1", DR3LK_PACK_PAGEABLE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "plain ok" in r.stdout, r.stderr[-3000:]
